@@ -1,0 +1,115 @@
+/*
+ * odtk_b200.h -- C ABI of the B200-native RetinaNet inference hot path.
+ *
+ * Drop-in boundary for NVIDIA/retinanet-examples (ODTK).  Every entry point is
+ * plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch,
+ * no C++ types.  The reference interface each function replaces is cited.
+ *
+ * Conventions shared by all post-processing entry points (they mirror
+ * odtk::cuda::*, which is also what the TensorRT plugins' enqueue() call,
+ * csrc/plugins/DecodePlugin.h:152-161, NMSPlugin.h:131-138):
+ *   - cub-style two-phase workspace: call with workspace == NULL or
+ *     workspace_size == 0 to get the required bytes (>= 0); the real call
+ *     returns 0 (csrc/cuda/decode.cu:53-72, nms.cu:87-105).  The return type is
+ *     64-bit (the reference returns int, which overflows for large batches).
+ *   - the caller owns every buffer; the library never allocates device memory
+ *     in these calls and never synchronises the host with the stream
+ *     (the reference blocks B*5+B times per forward, decode.cu:103, nms.cu:131).
+ *   - errors: a negative ODTK_E_* code; nothing is thrown across the boundary.
+ */
+#ifndef ODTK_B200_H_
+#define ODTK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODTK_OK 0
+#define ODTK_E_INVALID (-1)     /* bad argument (null pointer, size <= 0, ...)      */
+#define ODTK_E_WORKSPACE (-2)   /* workspace too small (reference: utils.h:55-57)    */
+#define ODTK_E_UNSUPPORTED (-3) /* size outside what the sm_100a kernels handle     */
+#define ODTK_E_CUDA (-4)        /* a CUDA runtime / driver call failed               */
+
+typedef void *odtk_stream_t; /* cudaStream_t */
+
+/* Limits of the sm_100a kernels (documented deviations from "any size"). */
+#define ODTK_MAX_TOP_N 4096      /* decode: top_n                                   */
+#define ODTK_MAX_NMS_COUNT 6144  /* nms: candidates per image                       */
+#define ODTK_MAX_DETECTIONS 1024 /* nms: detections_per_im                          */
+
+/* Library identification: returns a static string "odtk_b200 <version> sm_100a". */
+const char *odtk_b200_version(void);
+
+/* ---- decode -------------------------------------------------------------------
+ * Replaces odtk::cuda::decode (csrc/cuda/decode.h:30-35, decode.cu:44-171) and
+ * odtk::cuda::decode_rotate (decode_rotate.h:30-35, decode_rotate.cu:42-179).
+ *   inputs  = { scores [B, A*C, H, W], deltas [B, A*4|6, H, W] }  fp32, contiguous
+ *   outputs = { scores [B, top_n], boxes [B, top_n, 4|6], classes [B, top_n] } fp32
+ * Semantics: keep scores > score_thresh; if more than top_n survive, keep the
+ * top_n by (score desc, flat index asc) in that order, else keep flat-index order;
+ * decode each against anchors[4*a..] with the +1 width convention and the
+ * reference's clamps; zero the tails.  anchors is a HOST pointer (the reference
+ * takes std::vector<float>&; num_anchor_floats == 4*A, or 0 for raw deltas).    */
+long long odtk_decode(int batch, const void *const *inputs, void *const *outputs, size_t height,
+                      size_t width, size_t scale, size_t num_anchors, size_t num_classes,
+                      const float *anchors, size_t num_anchor_floats, float score_thresh, int top_n,
+                      void *workspace, size_t workspace_size, odtk_stream_t stream);
+
+long long odtk_decode_rotate(int batch, const void *const *inputs, void *const *outputs, size_t height,
+                             size_t width, size_t scale, size_t num_anchors, size_t num_classes,
+                             const float *anchors, size_t num_anchor_floats, float score_thresh,
+                             int top_n, void *workspace, size_t workspace_size, odtk_stream_t stream);
+
+/* Extended decode (B200-native addition): same maths, but the three outputs are
+ * written at element offset out_offset of rows that are out_stride entries long,
+ * so that the five pyramid levels land directly in the [B, 5*top_n] buffers the
+ * reference builds with torch.cat (odtk/model.py:164).  nbox = 4 or 6.          */
+long long odtk_decode_ex(int batch, const void *const *inputs, void *const *outputs, size_t height,
+                         size_t width, size_t scale, size_t num_anchors, size_t num_classes,
+                         const float *anchors, size_t num_anchor_floats, float score_thresh,
+                         int top_n, int nbox, size_t out_stride, size_t out_offset, void *workspace,
+                         size_t workspace_size, odtk_stream_t stream);
+
+/* ---- nms ----------------------------------------------------------------------
+ * Replaces odtk::cuda::nms (csrc/cuda/nms.h:28-31, nms.cu:82-160) and
+ * odtk::cuda::nms_rotate (nms_iou.h:28-31, nms_iou.cu:260-322).
+ *   inputs  = { scores [B, count], boxes [B, count, 4|6], classes [B, count] } fp32
+ *   outputs = { scores [B, D], boxes [B, D, 4|6], classes [B, D] }            fp32
+ * Semantics: drop scores <= 0, stable sort descending, greedy same-class
+ * suppression when overlap > nms_thresh (+1 widths; rotated: polygon clipping
+ * with the reference's quirks), emit the first min(D, n) entries of (kept...,
+ * suppressed...) exactly as the reference's second sort leaves them.           */
+long long odtk_nms(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                   int detections_per_im, float nms_thresh, void *workspace, size_t workspace_size,
+                   odtk_stream_t stream);
+
+long long odtk_nms_rotate(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                          int detections_per_im, float nms_thresh, void *workspace,
+                          size_t workspace_size, odtk_stream_t stream);
+
+/* Extended nms: nbox = 4|6; out_index (device int32 [B, D], may be NULL) receives
+ * the input position of every emitted entry (-1 for empty slots) -- the "kept
+ * indices" the parity tests compare bit-exactly.  fixed_angle != 0 rotates the
+ * max box with its OWN sin/cos instead of the candidate's (reference quirk,
+ * nms_iou.cu:188-192); 0 is bug-compatible.                                     */
+long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                      int detections_per_im, float nms_thresh, int nbox, int fixed_angle,
+                      int32_t *out_index, void *workspace, size_t workspace_size,
+                      odtk_stream_t stream);
+
+/* ---- per-kernel timing (B200-native addition; the reference has only a wall-clock
+ * Profiler without CUDA sync, odtk/utils.py:140-167) ------------------------------
+ * When enabled, every launch of a tagged kernel is bracketed by CUDA events on the
+ * launching stream.  Tags: 0 score filter, 1 select+decode, 2 nms, 3 conv, 4 loss.
+ * odtk_prof_get synchronises the device and returns summed ms and launch count.  */
+void odtk_prof_enable(int on);
+void odtk_prof_reset(void);
+int odtk_prof_get(int tag, double *total_ms, long long *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODTK_B200_H_ */

@@ -1,0 +1,92 @@
+"""Mirror of the reference's compiled extension module `odtk._C` (csrc/extensions.cpp:184-201):
+`decode`, `nms` with the same signatures, argument meaning, shapes, dtypes and error behaviour
+(RuntimeError on non-CUDA / non-contiguous input, extensions.cpp:42-44), implemented by the
+sm_100a kernels behind the C ABI.  `iou` and `Engine` (TensorRT) are outside the hot path."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _check_input(x, name):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if not x.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if x.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def decode(cls_head, box_head, anchors, scale, score_thresh, top_n, rotated=False,
+           out=None, out_offset=0):
+    """odtk._C.decode (csrc/extensions.cpp:69-115).
+    cls_head [B, A*C, H, W], box_head [B, A*4|6, H, W] fp32 CUDA contiguous; anchors: flat list of
+    4*A floats; returns [scores [B, top_n], boxes [B, top_n, 4|6], classes [B, top_n]].
+    `out`/`out_offset` (extension): write into rows of pre-allocated [B, S], [B, S, nbox], [B, S]
+    buffers at column out_offset (replaces the torch.cat of odtk/model.py:164)."""
+    _check_input(cls_head, "cls_head")
+    _check_input(box_head, "box_head")
+    L = _lib.lib()
+    nbox = 6 if rotated else 4
+    anchors = [float(a) for a in anchors]
+    batch = cls_head.size(0)
+    num_anchors = len(anchors) // 4 if anchors else box_head.size(1) // nbox
+    num_classes = cls_head.size(1) // num_anchors
+    height, width = cls_head.size(2), cls_head.size(3)
+    if out is None:
+        scores = torch.zeros((batch, top_n), dtype=torch.float32, device=cls_head.device)
+        boxes = torch.zeros((batch, top_n, nbox), dtype=torch.float32, device=cls_head.device)
+        classes = torch.zeros((batch, top_n), dtype=torch.float32, device=cls_head.device)
+        stride = top_n
+    else:
+        scores, boxes, classes = out
+        stride = scores.size(1)
+    inputs = _lib.ptr_array([cls_head.data_ptr(), box_head.data_ptr()])
+    outputs = _lib.ptr_array([scores.data_ptr(), boxes.data_ptr(), classes.data_ptr()])
+    anc = (ctypes.c_float * max(1, len(anchors)))(*anchors)
+    args = (batch, inputs, outputs, height, width, int(scale), num_anchors, num_classes, anc, len(anchors),
+            float(score_thresh), int(top_n), nbox, stride, int(out_offset))
+    size = _lib.check(L.odtk_decode_ex(*args, None, 0, None), "decode (workspace query)")
+    scratch = _workspace(size, cls_head.device)
+    _lib.check(L.odtk_decode_ex(*args, ctypes.c_void_p(scratch.data_ptr()), size, _stream()), "decode")
+    return [scores, boxes, classes]
+
+
+def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, return_index=False,
+        fixed_angle=False):
+    """odtk._C.nms (csrc/extensions.cpp:117-158).
+    scores [B, N], boxes [B, N, 4|6], classes [B, N] fp32 CUDA contiguous; returns
+    [scores [B, D], boxes [B, D, 4|6], classes [B, D]] (+ int32 kept positions [B, D] when
+    return_index, an extension used by the parity tests)."""
+    _check_input(scores, "scores")
+    _check_input(boxes, "boxes")
+    _check_input(classes, "classes")
+    L = _lib.lib()
+    nbox = 6 if rotated else 4
+    batch, count = scores.size(0), scores.size(1)
+    dev = scores.device
+    out_scores = torch.zeros((batch, detections_per_im), dtype=torch.float32, device=dev)
+    out_boxes = torch.zeros((batch, detections_per_im, nbox), dtype=torch.float32, device=dev)
+    out_classes = torch.zeros((batch, detections_per_im), dtype=torch.float32, device=dev)
+    out_index = torch.empty((batch, detections_per_im), dtype=torch.int32, device=dev) if return_index else None
+    inputs = _lib.ptr_array([scores.data_ptr(), boxes.data_ptr(), classes.data_ptr()])
+    outputs = _lib.ptr_array([out_scores.data_ptr(), out_boxes.data_ptr(), out_classes.data_ptr()])
+    idx_ptr = ctypes.c_void_p(out_index.data_ptr()) if return_index else None
+    args = (batch, inputs, outputs, count, int(detections_per_im), float(nms_thresh), nbox, int(bool(fixed_angle)),
+            idx_ptr)
+    size = _lib.check(L.odtk_nms_ex(*args, None, 0, None), "nms (workspace query)")
+    scratch = _workspace(size, dev)
+    _lib.check(L.odtk_nms_ex(*args, ctypes.c_void_p(scratch.data_ptr()), size, _stream()), "nms")
+    res = [out_scores, out_boxes, out_classes]
+    if return_index:
+        res.append(out_index)
+    return res

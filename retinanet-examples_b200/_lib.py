@@ -1,0 +1,69 @@
+"""ctypes loader for libodtk_b200.so (the C ABI declared in include/odtk_b200.h).
+
+The library is built in-tree by `make -C retinanet-examples_b200/csrc` (see
+__graft_entry__.build).  Loading fails loudly: there is no fallback implementation."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libodtk_b200.so")
+
+ODTK_OK = 0
+_ERRORS = {-1: "invalid argument", -2: "workspace is too small", -3: "size not supported by the sm_100a kernels",
+           -4: "CUDA runtime error"}
+
+_c_vpp = ctypes.POINTER(ctypes.c_void_p)
+_c_f32p = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); must list every symbol include/odtk_b200.h declares
+SIGNATURES = {
+    "odtk_b200_version": (ctypes.c_char_p, []),
+    "odtk_decode": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp] + [ctypes.c_size_t] * 5 +
+                    [_c_f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                     ctypes.c_void_p]),
+    "odtk_decode_rotate": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp] + [ctypes.c_size_t] * 5 +
+                           [_c_f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                            ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_decode_ex": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp] + [ctypes.c_size_t] * 5 +
+                       [_c_f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                        ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_nms": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_nms_rotate": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int,
+                                            ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_nms_ex": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_prof_enable": (None, [ctypes.c_int]),
+    "odtk_prof_reset": (None, []),
+    "odtk_prof_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Returns the loaded library; raises RuntimeError if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libodtk_b200.so is missing (%s): build it with `make -C retinanet-examples_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what):
+    if rc < 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, _ERRORS.get(int(rc), "unknown error"), rc))
+    return rc
+
+
+def ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])

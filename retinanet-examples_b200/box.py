@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's odtk/box.py for the inference hot path: anchor tables
+(setup-time, CPU) and the decode / nms / nms_rotated dispatchers, which here ALWAYS run the
+sm_100a kernels (the reference dispatches to odtk._C when torch.cuda.is_available(),
+odtk/box.py:262,315,373, and otherwise to a CPU fallback -- this package has no fallback)."""
+import math
+
+import numpy as np
+import torch
+
+from . import _C
+
+
+def generate_anchors(stride, ratio_vals, scales_vals, angles_vals=None):
+    """Anchor coordinates [A, 4] (x1, y1, x2, y2) for one pyramid level.
+    Reference: odtk/box.py:8-20; known answers: extras/cppapi/export.cpp:69-75."""
+    f = np.float32
+    nr, ns = len(ratio_vals), len(scales_vals)
+    scales = np.repeat(np.asarray(scales_vals, dtype=f), nr)[:, None]       # scale-major, ratio-minor
+    ratios = np.tile(np.asarray(ratio_vals, dtype=f), ns)
+    side = np.full((nr * ns, 2), stride, dtype=f)
+    w = np.sqrt(side[:, 0] * side[:, 1] / ratios).astype(f)
+    wh = np.stack([w, (w * ratios).astype(f)], axis=1)
+    lo = (f(0.5) * (side - wh * scales)).astype(f)
+    hi = (f(0.5) * (side + wh * scales)).astype(f)
+    return torch.from_numpy(np.concatenate([lo, hi], axis=1))
+
+
+def _order_points(quads):
+    """Order 4 corners as (top-left, top-right, bottom-right, bottom-left).
+    Reference: odtk/utils.py:15-31."""
+    out = []
+    for pt in quads:
+        by_x = pt[torch.argsort(pt[:, 0])]
+        left, right = by_x[:2], by_x[2:]
+        left = left[torch.argsort(left[:, 1])]
+        tl, bl = left[0], left[1]
+        dist = torch.cdist(tl[None], right)[0]
+        far = right[torch.argsort(dist, descending=True)]
+        br, tr = far[0], far[1]
+        out.append(torch.stack([tl, tr, br, bl]))
+    return torch.stack(out)
+
+
+def generate_anchors_rotated(stride, ratio_vals, scales_vals, angles_vals):
+    """Returns (anchors_axis [A*len(angles), 4], anchors_rotated [A*len(angles), 8]).
+    Only anchors_axis is consumed by decode (odtk/box.py:258-259, decode_rotate.cu:139).
+    Reference: odtk/box.py:23-64; known answers: extras/cppapi/export.cpp:79-85."""
+    f = torch.float32
+    nr, ns, na = len(ratio_vals), len(scales_vals), len(angles_vals)
+    scales = torch.tensor(scales_vals, dtype=f).repeat_interleave(nr)[:, None]
+    ratios = torch.tensor(list(ratio_vals) * ns, dtype=f)
+    side = torch.full((nr * ns, 2), float(stride), dtype=f)
+    w = torch.round(torch.sqrt(side[:, 0] * side[:, 1] / ratios))
+    wh = torch.stack([w, torch.round(w * ratios)], dim=1)
+    p0 = 0.5 * (side - wh * scales)
+    p2 = 0.5 * (side + wh * scales) - 1
+    p1 = p0 + (p2 - p0) * torch.tensor([0.0, 1.0])
+    p3 = p0 + (p2 - p0) * torch.tensor([1.0, 0.0])
+    angles = torch.tensor(angles_vals, dtype=f)
+    rot = torch.stack([torch.stack([torch.cos(angles), torch.sin(angles)], dim=1),
+                       torch.stack([-torch.sin(angles), torch.cos(angles)], dim=1)], dim=1)  # [na, 2, 2]
+    half = stride / 2 - 0.5
+
+    def spin(pts):
+        r = torch.matmul(rot, pts.t() - half) + half            # [na, 2, n]
+        return r.permute(0, 2, 1).contiguous().view(-1, 2)
+
+    corners = torch.stack([spin(p0), spin(p1), spin(p2), spin(p3)], dim=1)
+    anchors_axis = torch.cat([p0.repeat(na, 1), p2.repeat(na, 1)], dim=1)
+    anchors_rotated = _order_points(corners).view(-1, 8)
+    return anchors_axis, anchors_rotated
+
+
+def decode(all_cls_head, all_box_head, stride=1, threshold=0.05, top_n=1000, anchors=None, rotated=False):
+    """Box decoding and filtering of one pyramid level for the whole batch.
+    Reference: odtk/box.py:255-264 -> odtk._C.decode (the `.float()` casts are kept)."""
+    if rotated:
+        anchors = anchors[0]
+    flat = anchors.reshape(-1).tolist() if anchors is not None else []
+    return _C.decode(all_cls_head.float().contiguous(), all_box_head.float().contiguous(), flat, stride,
+                     threshold, top_n, rotated)
+
+
+def nms(all_scores, all_boxes, all_classes, nms=0.5, ndetections=100):
+    """Per-image non-maximum suppression.  Reference: odtk/box.py:312-317 -> odtk._C.nms."""
+    return _C.nms(all_scores.float().contiguous(), all_boxes.float().contiguous(),
+                  all_classes.float().contiguous(), nms, ndetections, False)
+
+
+def nms_rotated(all_scores, all_boxes, all_classes, nms=0.5, ndetections=100):
+    """Rotated-box NMS.  Reference: odtk/box.py:370-375 -> odtk._C.nms(..., rotated=True)."""
+    return _C.nms(all_scores.float().contiguous(), all_boxes.float().contiguous(),
+                  all_classes.float().contiguous(), nms, ndetections, True)
+
+
+DEFAULT_RATIOS = [1.0, 2.0, 0.5]
+DEFAULT_SCALES = [4 * 2 ** (i / 3) for i in range(3)]
+DEFAULT_ANGLES = [-math.pi / 6, 0, math.pi / 6]

@@ -1,0 +1,65 @@
+// common.cuh -- small device/host helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/odtk_b200.h"
+
+#define ODTK_ALIGN 256  // every workspace sub-buffer is 256-B aligned (reference: utils.h:28)
+
+static inline size_t odtk_align_up(size_t x) { return (x + ODTK_ALIGN - 1) / ODTK_ALIGN * ODTK_ALIGN; }
+
+// Monotone float -> uint32 key; larger key == larger float.  This is the transform
+// cub::DeviceRadixSort applies to float keys, so "descending, stable" in the
+// reference (decode.cu:111, nms.cu:135) == descending on (key, ~position).
+__host__ __device__ __forceinline__ uint32_t odtk_float_key(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b;
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float odtk_key_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ float4 odtk_ld_stream_f4(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float odtk_ld_stream_f1(const float *p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// In-place bitonic sort, DESCENDING, of P (power of two) 64-bit keys in shared memory by
+// the whole CTA.  Keys are unique (composite of value and position) so the unstable
+// network reproduces the reference's stable radix order exactly.
+__device__ __forceinline__ void odtk_bitonic_desc_u64(unsigned long long *s, int P) {
+  const int T = blockDim.x, t = threadIdx.x;
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < (P >> 1); i += T) {
+        int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        int hi = lo | j;
+        bool desc = ((lo & k) == 0);
+        unsigned long long a = s[lo], b = s[hi];
+        if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ int odtk_next_pow2(int x) {
+  int p = 32;
+  while (p < x) p <<= 1;
+  return p;
+}

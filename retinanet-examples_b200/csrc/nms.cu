@@ -1,0 +1,398 @@
+// nms.cu -- batched per-image greedy NMS (axis-aligned and rotated) for sm_100a.
+//
+// Replaces odtk::cuda::nms + nms_kernel (reference csrc/cuda/nms.cu:44-160) and
+// odtk::cuda::nms_rotate + nms_rotate_kernel (csrc/cuda/nms_iou.cu:114-322).  The
+// reference handles ONE image at a time: cub select -> host sync -> gather -> 32-bit radix
+// sort -> a single 1024-thread block that walks ALL n candidates serially with a
+// __syncthreads each -> second radix sort -> gathers.  Here the whole batch is one launch,
+// one CTA per image, nothing leaves shared memory:
+//
+//   1. composite keys (score key << 32 | ~position) for scores > 0, bitonic network in
+//      shared memory == the reference's stable descending radix sort;
+//   2. boxes / classes gathered once into shared memory in rank order;
+//   3. greedy loop over KEEPERS only (the reference loops over every candidate): each
+//      iteration broadcasts the keeper, all threads test their own ranks (class gate
+//      first, IEEE division, +1 widths), and a warp-reduced atomicMin finds the next
+//      survivor.  The loop stops at detections_per_im keepers -- exact, because the output
+//      is the first D entries of (kept..., suppressed...) and later candidates can never
+//      change earlier decisions (SURVEY.md section 8 note N1);
+//   4. if fewer than D were kept the tail is the first suppressed candidates in rank order
+//      with score 0 and their boxes/classes, exactly what the reference's second sort
+//      leaves there (nms.cu:146-156).
+//
+// Arithmetic: fp32, IEEE division, no FMA contraction (-fmad=false): the PyTorch path is
+// the parity target, not the reference's --use_fast_math build.
+#include <limits.h>
+
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kMaxCount = ODTK_MAX_NMS_COUNT;  // 6144
+constexpr int kMaxRanks = kMaxCount / kThreads;  // ranks per thread
+constexpr int kMaxDet = ODTK_MAX_DETECTIONS;
+
+struct f2 { float x, y; };
+struct line_t { float a, b, c; };
+
+__device__ __forceinline__ line_t make_line(f2 v1, f2 v2) {  // nms_iou.cu:87
+  line_t l;
+  l.a = v2.y - v1.y;
+  l.b = v1.x - v2.x;
+  l.c = v2.x * v1.y - v2.y * v1.x;
+  return l;
+}
+__device__ __forceinline__ float line_call(line_t l, f2 v) { return l.a * v.x + l.b * v.y + l.c; }
+__device__ __forceinline__ f2 line_isect(line_t l, line_t o) {  // nms_iou.cu:93-96
+  float w = l.a * o.b - l.b * o.a;
+  f2 r;
+  r.x = (l.b * o.c - l.c * o.b) / w;
+  r.y = (l.c * o.a - l.a * o.c) / w;
+  return r;
+}
+
+// Sutherland-Hodgman clip of `inter` (<= 8 points) against the 4 edges of mrect, then
+// shoelace: nms_iou.cu:114-169, same operation order.  Writes beyond 8 points (undefined
+// in the reference) are dropped.
+__device__ float intersection_area(const f2 *mrect, f2 *inter) {
+  int count = 4;
+  for (int i = 0; i < 4; i++) {
+    float lv[8];
+    line_t l1 = make_line(mrect[i], mrect[(i + 1) & 3]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) lv[j] = (j < count) ? line_call(l1, inter[j]) : 0.0f;
+    f2 nw[8];
+    int temp = count;
+    count = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j < temp) {
+        int jn = (j + 1 == temp) ? 0 : j + 1;  // rotateLeft(count)
+        float lvs = lv[jn];
+        if (lv[j] <= 0) {
+          if (count < 8) nw[count] = inter[j];
+          count++;
+        }
+        if ((lv[j] * lvs) <= 0) {
+          line_t l2 = make_line(inter[j], inter[jn]);
+          if (count < 8) nw[count] = line_isect(l1, l2);
+          count++;
+        }
+      }
+    }
+    if (count > 8) count = 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < count) inter[k] = nw[k];
+  }
+  float area = 0.0f;
+  if (count > 2) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < count) {
+        int kn = (k + 1 == count) ? 0 : k + 1;
+        area += inter[k].x * inter[kn].y - inter[k].y * inter[kn].x;
+      }
+    }
+  }
+  return fabsf(area / 2.0f);
+}
+
+// nms_iou.cu:182-248.  ib / mb = (x1,y1,x2,y2,sin,cos).
+__device__ float rotated_overlap(const float *ib, const float *mb, int fixed_angle) {
+  const float is = ib[4], ic = ib[5];
+  const float ms = fixed_angle ? mb[4] : ib[4], mc = fixed_angle ? mb[5] : ib[5];
+  f2 inter[8], irect[4], mrect[4];
+  const float icx = (ib[0] + ib[2]) / 2.0f, icy = (ib[1] + ib[3]) / 2.0f;
+  const float mcx = (mb[0] + mb[2]) / 2.0f, mcy = (mb[1] + mb[3]) / 2.0f;
+  const float ibx[4] = {ib[0] - icx, ib[2] - icx, ib[2] - icx, ib[0] - icx};
+  const float iby[4] = {ib[1] - icy, ib[1] - icy, ib[3] - icy, ib[3] - icy};
+  const float mbx[4] = {mb[0] - mcx, mb[2] - mcx, mb[2] - mcx, mb[0] - mcx};
+  const float mby[4] = {mb[1] - mcy, mb[1] - mcy, mb[3] - mcy, mb[3] - mcy};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    float ix = (ibx[b] * ic - iby[b] * is) + icx;
+    float iy = (iby[b] * ic + ibx[b] * is) + icy;
+    float mx = (mbx[b] * mc - mby[b] * ms) + mcx;
+    float my = (mby[b] * mc + mbx[b] * ms) + mcy;
+    float px = (ix == mx) ? 0.001f : 0.0f;
+    float py = (iy == my) ? 0.001f : 0.0f;
+    inter[b].x = ix + px; inter[b].y = iy + py;
+    irect[b].x = ix; irect[b].y = iy;
+    mrect[b].x = mx; mrect[b].y = my;
+  }
+#pragma unroll
+  for (int b = 4; b < 8; b++) { inter[b].x = -1.0f; inter[b].y = -1.0f; }
+  float ia = intersection_area(mrect, inter);
+  float irect_area = 0.0f, mrect_area = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int kn = (k + 1) & 3;
+    irect_area += irect[k].x * irect[kn].y - irect[k].y * irect[kn].x;
+    mrect_area += mrect[k].x * mrect[kn].y - mrect[k].y * mrect[kn].x;
+  }
+  float ua = (fabsf(irect_area) + fabsf(mrect_area)) / 2.0f;
+  float overlap;
+  if (isnan(ia) && isnan(ua)) overlap = 1.0f;
+  else if (isnan(ia)) overlap = 0.0f;
+  else overlap = ia / (ua - ia);
+  return overlap;
+}
+
+// nms.cu:57-69
+__device__ __forceinline__ float aligned_overlap(const float *ib, const float *mb) {
+  float x1 = fmaxf(ib[0], mb[0]);
+  float y1 = fmaxf(ib[1], mb[1]);
+  float x2 = fminf(ib[2], mb[2]);
+  float y2 = fminf(ib[3], mb[3]);
+  float w = fmaxf(0.0f, x2 - x1 + 1);
+  float h = fmaxf(0.0f, y2 - y1 + 1);
+  float iarea = (ib[2] - ib[0] + 1) * (ib[3] - ib[1] + 1);
+  float marea = (mb[2] - mb[0] + 1) * (mb[3] - mb[1] + 1);
+  float inter = w * h;
+  return inter / (iarea + marea - inter);
+}
+
+struct NmsParams {
+  const float *scores, *boxes, *classes;  // [B,count], [B,count,NBOX], [B,count]
+  float *out_scores, *out_boxes, *out_classes;
+  int32_t *out_index;  // may be NULL
+  int count, detections;
+  float thresh;
+  int fixed_angle;
+};
+
+// dynamic shared memory carve-up (bytes); the sort buffer is aliased by the gathered data
+template <int NBOX>
+struct NmsSmem {
+  static constexpr size_t box_bytes(int n) { return (size_t)n * NBOX * sizeof(float); }
+  static size_t total(int count) {
+    size_t sort_b = (size_t)odtk_next_pow2(count) * 8;
+    size_t data_b = box_bytes(count) + (size_t)count * 4 /*cls*/ + (size_t)count * 4 /*idx*/;
+    return (sort_b > data_b ? sort_b : data_b) + 16;
+  }
+};
+
+template <int NBOX>
+__global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_kept[kMaxDet];
+  __shared__ int s_tail[kMaxDet];
+  __shared__ int s_next[3];
+  __shared__ int s_wsum[32];
+  __shared__ int s_n;
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int img = blockIdx.x;
+  const int count = p.count, D = p.detections;
+  const float *sc = p.scores + (long long)img * count;
+  const float *bx = p.boxes + (long long)img * count * NBOX;
+  const float *cl = p.classes + (long long)img * count;
+
+  // ---- 1. keys + sort (nms.cu:125-137) ------------------------------------------------
+  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
+  const int P = odtk_next_pow2(count);
+  if (t == 0) { s_n = 0; s_next[0] = s_next[1] = s_next[2] = INT_MAX; }
+  __syncthreads();
+  int nvalid = 0;
+  for (int i = t; i < P; i += kThreads) {
+    unsigned long long c = 0ull;
+    if (i < count) {
+      float v = sc[i];
+      if (v > 0.0f) { c = ((unsigned long long)odtk_float_key(v) << 32) | (uint32_t)(~(uint32_t)i); nvalid++; }
+    }
+    skey[i] = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+  if (lane == 0 && nvalid) atomicAdd(&s_n, nvalid);
+  __syncthreads();
+  const int n = s_n;
+  odtk_bitonic_desc_u64(skey, P);
+
+  // ---- 2. gather in rank order -----------------------------------------------------------
+  int my_idx[kMaxRanks];
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; k++) {
+    int r = t + k * kThreads;
+    my_idx[k] = (r < n) ? (int)(~(uint32_t)skey[r]) : -1;
+  }
+  __syncthreads();  // the sort buffer is dead from here on
+  float *sbox = reinterpret_cast<float *>(smem_raw);
+  int *scls = reinterpret_cast<int *>(smem_raw + (size_t)count * NBOX * sizeof(float));
+  int *sidx = scls + count;
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; k++) {
+    int r = t + k * kThreads;
+    if (r < n) {
+      int i = my_idx[k];
+      if (NBOX == 4) {
+        float4 b = *reinterpret_cast<const float4 *>(bx + (long long)i * 4);
+        *reinterpret_cast<float4 *>(sbox + r * 4) = b;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NBOX; q += 2) {
+          float2 b = *reinterpret_cast<const float2 *>(bx + (long long)i * NBOX + q);
+          *reinterpret_cast<float2 *>(sbox + r * NBOX + q) = b;
+        }
+      }
+      scls[r] = (int)cl[i];  // float -> int cast as nms.cu:55-56
+      sidx[r] = i;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. greedy over keepers (nms_kernel, nms.cu:49-79) ---------------------------------
+  unsigned alive = 0;  // bit k: rank t + k*1024 not suppressed
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; k++)
+    if (t + k * kThreads < n) alive |= 1u << k;
+  const int nd = n < D ? n : D;
+  int kept = 0, m = (n > 0) ? 0 : INT_MAX, iter = 0;
+  while (m < n) {
+    if (t == 0) s_kept[kept] = m;
+    kept++;
+    if (kept >= D) break;
+    if (t == 0) s_next[(iter + 1) % 3] = INT_MAX;
+    float mb[NBOX];
+#pragma unroll
+    for (int q = 0; q < NBOX; q++) mb[q] = sbox[m * NBOX + q];
+    const int mcls = scls[m];
+    int first = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++) {
+      int r = t + k * kThreads;
+      if (r > m && ((alive >> k) & 1u)) {
+        bool sup = false;
+        if (scls[r] == mcls) {
+          float ib[NBOX];
+#pragma unroll
+          for (int q = 0; q < NBOX; q++) ib[q] = sbox[r * NBOX + q];
+          float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
+          sup = ov > p.thresh;
+        }
+        if (sup) alive &= ~(1u << k);
+        else if (r < first) first = r;
+      }
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    if (lane == 0 && first != INT_MAX) atomicMin(&s_next[iter % 3], first);
+    __syncthreads();
+    m = s_next[iter % 3];
+    iter++;
+  }
+  __syncthreads();
+
+  // ---- 4. tail: first suppressed ranks, only when fewer than min(D, n) were kept ---------
+  if (kept < nd) {
+    // here the loop ran to exhaustion: every rank < n is either kept (alive) or suppressed
+    const int need = nd - kept;
+    int base = 0;
+    for (int k = 0; k < kMaxRanks && base < need; k++) {
+      int r = t + k * kThreads;
+      bool dead = (r < n) && !((alive >> k) & 1u);
+      unsigned bal = __ballot_sync(0xffffffffu, dead);
+      int wcount = __popc(bal);
+      __syncthreads();
+      if (lane == 0) s_wsum[warp] = wcount;
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int w = 0; w < 32; w++) {
+        int v = s_wsum[w];
+        if (w < warp) woff += v;
+        tot += v;
+      }
+      int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
+      if (dead && pos < need) s_tail[pos] = r;
+      base += tot;
+    }
+    __syncthreads();
+  }
+
+  // ---- 5. outputs (nms.cu:150-156) --------------------------------------------------------
+  float *os = p.out_scores + (long long)img * D;
+  float *ob = p.out_boxes + (long long)img * D * NBOX;
+  float *oc = p.out_classes + (long long)img * D;
+  int32_t *oi = p.out_index ? p.out_index + (long long)img * D : nullptr;
+  for (int j = t; j < D; j += kThreads) {
+    if (j < nd) {
+      int r = (j < kept) ? s_kept[j] : s_tail[j - kept];
+      int i = sidx[r];
+      os[j] = (j < kept) ? sc[i] : 0.0f;
+#pragma unroll
+      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = sbox[r * NBOX + q];
+      oc[j] = cl[i];
+      if (oi) oi[j] = i;
+    } else {
+      os[j] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = 0.0f;
+      oc[j] = 0.0f;
+      if (oi) oi[j] = -1;
+    }
+  }
+}
+
+template <int NBOX>
+long long launch_nms(const NmsParams &p, int batch, cudaStream_t stream) {
+  size_t smem = NmsSmem<NBOX>::total(p.count);
+  static bool configured = false;  // per template instance
+  if (!configured) {
+    if (cudaFuncSetAttribute(nms_batched_kernel<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)NmsSmem<NBOX>::total(kMaxCount)) != cudaSuccess)
+      return ODTK_E_CUDA;
+    configured = true;
+  }
+  {
+    OdtkProfScope prof(ODTK_PROF_NMS, stream);
+    nms_batched_kernel<NBOX><<<batch, kThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                                 int detections_per_im, float nms_thresh, int nbox, int fixed_angle,
+                                 int32_t *out_index, void *workspace, size_t workspace_size,
+                                 odtk_stream_t stream) {
+  if (batch <= 0 || count == 0 || detections_per_im <= 0) return ODTK_E_INVALID;
+  if (nbox != 4 && nbox != 6) return ODTK_E_INVALID;
+  if (count > (size_t)kMaxCount || detections_per_im > kMaxDet) return ODTK_E_UNSUPPORTED;
+  // Everything lives in shared memory; a token workspace keeps the two-phase convention.
+  if (!workspace || !workspace_size) return ODTK_ALIGN;
+  if (workspace_size < ODTK_ALIGN) return ODTK_E_WORKSPACE;
+  if (!inputs || !outputs || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0] || !outputs[1] ||
+      !outputs[2])
+    return ODTK_E_INVALID;
+  if (((uintptr_t)inputs[1]) % (nbox == 4 ? 16 : 8)) return ODTK_E_INVALID;  // vector loads of the boxes
+  NmsParams p;
+  p.scores = (const float *)inputs[0];
+  p.boxes = (const float *)inputs[1];
+  p.classes = (const float *)inputs[2];
+  p.out_scores = (float *)outputs[0];
+  p.out_boxes = (float *)outputs[1];
+  p.out_classes = (float *)outputs[2];
+  p.out_index = out_index;
+  p.count = (int)count;
+  p.detections = detections_per_im;
+  p.thresh = nms_thresh;
+  p.fixed_angle = fixed_angle;
+  return nbox == 4 ? launch_nms<4>(p, batch, (cudaStream_t)stream) : launch_nms<6>(p, batch, (cudaStream_t)stream);
+}
+
+extern "C" long long odtk_nms(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                              int detections_per_im, float nms_thresh, void *workspace,
+                              size_t workspace_size, odtk_stream_t stream) {
+  return odtk_nms_ex(batch, inputs, outputs, count, detections_per_im, nms_thresh, 4, 0, nullptr, workspace,
+                     workspace_size, stream);
+}
+
+extern "C" long long odtk_nms_rotate(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                                     int detections_per_im, float nms_thresh, void *workspace,
+                                     size_t workspace_size, odtk_stream_t stream) {
+  return odtk_nms_ex(batch, inputs, outputs, count, detections_per_im, nms_thresh, 6, 0, nullptr, workspace,
+                     workspace_size, stream);
+}
