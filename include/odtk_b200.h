@@ -73,6 +73,23 @@ long long odtk_decode_ex(int batch, const void *const *inputs, void *const *outp
                          int top_n, int nbox, size_t out_stride, size_t out_offset, void *workspace,
                          size_t workspace_size, odtk_stream_t stream);
 
+/* All pyramid levels of the whole batch in three launches (B200-native addition; the
+ * reference calls decode once per level, odtk/model.py:153-161, and torch.cat's the
+ * results, :164).  Level l writes columns [out_offset + l*top_n, +top_n) of the
+ * [B, out_stride] outputs.  anchors in odtk_level_t is a HOST pointer (4*A floats). */
+#define ODTK_MAX_LEVELS 8
+typedef struct {
+  const void *scores;  /* device [B, A*C, H, W] fp32 */
+  const void *deltas;  /* device [B, A*nbox, H, W] fp32 */
+  size_t height, width, scale;
+  const float *anchors; /* host, 4*A floats (ignored when num_anchor_floats == 0) */
+} odtk_level_t;
+
+long long odtk_decode_levels(int batch, int num_levels, const odtk_level_t *levels, size_t num_anchors,
+                             size_t num_classes, size_t num_anchor_floats, float score_thresh, int top_n,
+                             int nbox, void *const *outputs, size_t out_stride, size_t out_offset,
+                             void *workspace, size_t workspace_size, odtk_stream_t stream);
+
 /* ---- nms ----------------------------------------------------------------------
  * Replaces odtk::cuda::nms (csrc/cuda/nms.h:28-31, nms.cu:82-160) and
  * odtk::cuda::nms_rotate (nms_iou.h:28-31, nms_iou.cu:260-322).

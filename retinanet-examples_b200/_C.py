@@ -61,6 +61,42 @@ def decode(cls_head, box_head, anchors, scale, score_thresh, top_n, rotated=Fals
     return [scores, boxes, classes]
 
 
+def decode_levels(cls_heads, box_heads, anchors, scales, score_thresh, top_n, rotated=False):
+    """All pyramid levels of the batch in three launches (B200-native addition, see
+    odtk_decode_levels in include/odtk_b200.h).  cls_heads / box_heads: lists of per-level
+    tensors as for `decode`; anchors: list of flat per-level lists; scales: per-level strides.
+    Returns [scores [B, L*top_n], boxes [B, L*top_n, 4|6], classes [B, L*top_n]] == the torch.cat
+    over levels of the per-level `decode` results (odtk/model.py:164)."""
+    L = _lib.lib()
+    nl = len(cls_heads)
+    nbox = 6 if rotated else 4
+    for c, b in zip(cls_heads, box_heads):
+        _check_input(c, "cls_head")
+        _check_input(b, "box_head")
+    batch, dev = cls_heads[0].size(0), cls_heads[0].device
+    na_floats = len(anchors[0]) if anchors and anchors[0] is not None else 0
+    num_anchors = na_floats // 4 if na_floats else box_heads[0].size(1) // nbox
+    num_classes = cls_heads[0].size(1) // num_anchors
+    levels = (_lib.Level * nl)()
+    keep = []
+    for i in range(nl):
+        anc = (ctypes.c_float * max(1, na_floats))(*[float(a) for a in (anchors[i] if na_floats else [])])
+        keep.append(anc)
+        levels[i].scores, levels[i].deltas = cls_heads[i].data_ptr(), box_heads[i].data_ptr()
+        levels[i].height, levels[i].width, levels[i].scale = cls_heads[i].size(2), cls_heads[i].size(3), int(scales[i])
+        levels[i].anchors = ctypes.cast(anc, ctypes.POINTER(ctypes.c_float))
+    scores = torch.empty((batch, nl * top_n), dtype=torch.float32, device=dev)
+    boxes = torch.empty((batch, nl * top_n, nbox), dtype=torch.float32, device=dev)
+    classes = torch.empty((batch, nl * top_n), dtype=torch.float32, device=dev)
+    outputs = _lib.ptr_array([scores.data_ptr(), boxes.data_ptr(), classes.data_ptr()])
+    args = (batch, nl, ctypes.cast(levels, ctypes.c_void_p), num_anchors, num_classes, na_floats, float(score_thresh),
+            int(top_n), nbox, outputs, nl * top_n, 0)
+    size = _lib.check(L.odtk_decode_levels(*args, None, 0, None), "decode_levels (workspace query)")
+    scratch = _workspace(size, dev)
+    _lib.check(L.odtk_decode_levels(*args, ctypes.c_void_p(scratch.data_ptr()), size, _stream()), "decode_levels")
+    return [scores, boxes, classes]
+
+
 def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, return_index=False,
         fixed_angle=False):
     """odtk._C.nms (csrc/extensions.cpp:117-158).

@@ -27,6 +27,10 @@ SIGNATURES = {
     "odtk_decode_ex": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp] + [ctypes.c_size_t] * 5 +
                        [_c_f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_decode_levels": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                               ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
+                                               ctypes.c_int, _c_vpp, ctypes.c_size_t, ctypes.c_size_t,
+                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_nms": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_nms_rotate": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int,
@@ -38,6 +42,14 @@ SIGNATURES = {
     "odtk_prof_reset": (None, []),
     "odtk_prof_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
 }
+
+
+
+class Level(ctypes.Structure):
+    """odtk_level_t (include/odtk_b200.h)."""
+    _fields_ = [("scores", ctypes.c_void_p), ("deltas", ctypes.c_void_p), ("height", ctypes.c_size_t),
+                ("width", ctypes.c_size_t), ("scale", ctypes.c_size_t), ("anchors", _c_f32p)]
+
 
 _LIB = None
 

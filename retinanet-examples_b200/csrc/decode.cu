@@ -1,27 +1,33 @@
 // decode.cu -- score filter + exact top-n + anchor box decode for sm_100a.
 //
 // Replaces odtk::cuda::decode / decode_rotate (reference csrc/cuda/decode.cu:44-171,
-// decode_rotate.cu:42-179), which run, PER IMAGE and with a host sync in between,
+// decode_rotate.cu:42-179), which run, PER IMAGE and PER LEVEL with a host sync in between,
 // thrust::transform -> cub::DeviceSelect -> D2H count -> gather -> cub radix sort ->
-// thrust::transform.  Here one level of the whole batch is two launches and no host sync:
+// thrust::transform.  Here ALL pyramid levels of the whole batch are three launches and no
+// host sync (the per-level reference entry points are the one-level special case):
 //
-//   K1 score_filter_kernel   HBM-bound streaming pass over [B, A*C*H*W] fp32 (128-bit
-//                            L1-bypassing loads, 4 in flight per lane).  Survivors
-//                            (score > thresh, ~0.5 %) are staged per warp in shared
-//                            memory and flushed with ONE global atomic per >= 32 of them
-//                            into a per-image candidate list (key, flat index), while a
-//                            2048-bin histogram of the score keys is accumulated.
-//   K2 select_decode_kernel  one CTA per image: the histogram gives the bin that holds
-//                            the top_n-th score; only candidates at or above it (about
-//                            top_n of them) are pulled into shared memory and ordered
-//                            with a bitonic network on the unique composite key
-//                            (score key, ~flat index) == the reference's stable order;
-//                            then every kept index is decoded (fp32, IEEE, no FMA
-//                            contraction, same operation order as decode.cu:133-156).
+//   K1 score_filter_kernel   HBM-bound streaming pass over every [B, A*C*H*W] fp32 score map
+//                            (128-bit L1-bypassing loads, register double-buffered so >= 4
+//                            are always in flight per lane).  Survivors (score > thresh,
+//                            ~0.5 %) are staged per warp in shared memory and flushed with
+//                            ONE global atomic per >= 32 of them into a per-(level,image)
+//                            candidate list (score key, flat index); a 2048-bin histogram of
+//                            the score keys is accumulated on the side.
+//   K2 gather_top_kernel     many CTAs per (level,image): the histogram gives the bin b* that
+//                            holds the top_n-th score; candidates in bins >= b* (about top_n
+//                            of them) are compacted into a short list (block-aggregated
+//                            atomics, batched loads).
+//   K3 select_decode_kernel  one CTA per (level,image): bitonic network on the unique
+//                            composite key (score key, ~flat index) == the reference's stable
+//                            order; every kept index is decoded in fp32, IEEE, no FMA
+//                            contraction, same operation order as decode.cu:133-156, and
+//                            written straight into the concatenated [B, L*top_n] outputs.
 //
-// Exactness never depends on the data: if the candidate list overflows, or a histogram
-// bin holds more ties than the sort capacity, K2 falls back to an 8-pass radix select on
-// the composite key (slow, exact).  Compile with -fmad=false (see Makefile).
+// Exactness never depends on the data: if a candidate list overflows, or a histogram bin holds
+// more ties than the sort capacity, K3 falls back to an 8-pass radix select on the composite
+// key (slow, exact).  Compile with -fmad=false (see Makefile).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "prof.cuh"
 
@@ -29,26 +35,40 @@ namespace {
 
 constexpr int kHistBins = 2048;
 constexpr int kSortCap = ODTK_MAX_TOP_N;  // 4096 keys of 8 B = 32 KB shared
-constexpr int kMaxAnchors = 32;           // anchor table travels as a kernel parameter
+constexpr int kMaxAnchors = 32;           // anchor tables travel as kernel parameters
+constexpr int kMaxLevels = ODTK_MAX_LEVELS;
 constexpr int kFilterThreads = 256;
 constexpr int kWarpsPerBlock = kFilterThreads / 32;
 constexpr int kTile = 512;                 // elements per warp per iteration (4 x float4 x 32)
 constexpr int kStage = 32 + kTile;         // per-warp staging entries
+constexpr int kGatherSlices = 16;
+constexpr int kGatherThreads = 256;
 
-struct AnchorTable {
-  float v[4 * kMaxAnchors];
+struct LevelDesc {
+  const float *scores;  // [B, n]
+  const float *deltas;  // [B, A*NBOX*H*W]
+  long long n;          // A*C*H*W
+  long long cand_off;   // first candidate entry of this level (entries), cap entries per image
+  long long cap;
+  int height, width, scale, out_offset;
+  int blk_begin, blk_per_img;  // filter-kernel block range of this level
+  int vec;                     // 128-bit loads allowed
+  int pad;
 };
 
-struct FilterParams {
-  const float *scores;   // [B, n]
-  long long n;           // elements per image
+struct DecodeParams {
+  LevelDesc lv[kMaxLevels];
+  float anchors[kMaxLevels][4 * kMaxAnchors];
+  int num_levels, batch, num_anchors, num_classes, has_anchors, top_n, shift;
   float thresh;
   uint32_t key_thresh;
-  int shift;             // histogram bin = min((key - key_thresh) >> shift, kHistBins-1)
-  int *counts;           // [B]
-  uint32_t *hist;        // [B, kHistBins]
-  uint2 *cand;           // [B, cap]  (x = score key, y = flat index)
-  long long cap;
+  int *counts;                 // [L*B]
+  uint32_t *hist;              // [L*B, kHistBins]
+  uint2 *cand;                 // per level: [B, cap_l]  (x = score key, y = flat index)
+  int *selcount;               // [L*B]
+  unsigned long long *sel;     // [L*B, kSortCap] composites gathered by K2
+  float *out_scores, *out_boxes, *out_classes;
+  long long out_stride;
 };
 
 __device__ __forceinline__ int hist_bin(uint32_t key, uint32_t key_thresh, int shift) {
@@ -57,15 +77,24 @@ __device__ __forceinline__ int hist_bin(uint32_t key, uint32_t key_thresh, int s
 }
 
 // ------------------------------------------------------------------------------------
-// K1: streaming filter.  grid = (blocks, B), block = 256.
-template <bool VEC>
-__global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(FilterParams p) {
+// K1: streaming filter.  grid = sum over levels of B * blk_per_img, block = 256.
+__global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(const __grid_constant__ DecodeParams p) {
   __shared__ uint2 stage[kWarpsPerBlock][kStage];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int img = blockIdx.y;
-  const float *s = p.scores + (long long)img * p.n;
-  uint2 *cand = p.cand + (long long)img * p.cap;
-  uint32_t *hist = p.hist + (long long)img * kHistBins;
+  int level = 0;
+#pragma unroll 1
+  for (int l = 1; l < p.num_levels; l++)
+    if ((int)blockIdx.x >= p.lv[l].blk_begin) level = l;
+  const LevelDesc &L = p.lv[level];
+  const int rel = (int)blockIdx.x - L.blk_begin;
+  const int img = rel / L.blk_per_img, blk = rel - img * L.blk_per_img;
+  const int slot = level * p.batch + img;
+  const long long n = L.n;
+  const float thresh = p.thresh;
+  const float *s = L.scores + (long long)img * n;
+  uint2 *cand = p.cand + L.cand_off + (long long)img * L.cap;
+  const long long cap = L.cap;
+  uint32_t *hist = p.hist + (long long)slot * kHistBins;
   uint2 *st = stage[warp];
   const unsigned lt_mask = (1u << lane) - 1u;
   int nstaged = 0;  // warp-uniform
@@ -74,12 +103,12 @@ __global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(FilterPara
     if (nstaged > 0) {
       __syncwarp();
       int base = 0;
-      if (lane == 0) base = atomicAdd(p.counts + img, nstaged);
+      if (lane == 0) base = atomicAdd(p.counts + slot, nstaged);
       base = __shfl_sync(0xffffffffu, base, 0);
       for (int j = lane; j < nstaged; j += 32) {
         uint2 c = st[j];
         long long dst = (long long)base + j;
-        if (dst < p.cap) cand[dst] = c;
+        if (dst < cap) cand[dst] = c;
         atomicAdd(hist + hist_bin(c.x, p.key_thresh, p.shift), 1u);
       }
       __syncwarp();
@@ -94,61 +123,159 @@ __global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(FilterPara
     }
   };
 
-  const long long ntiles = (p.n + kTile - 1) / kTile;
-  const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
-  for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < ntiles; t += wstride) {
-    const long long e0 = t * kTile;
-    if (VEC) {
-      float4 v[4];
+  const long long ntiles = (n + kTile - 1) / kTile;
+  const long long wstride = (long long)L.blk_per_img * kWarpsPerBlock;
+  long long t = (long long)blk * kWarpsPerBlock + warp;
+  if (L.vec) {
+    auto load_tile = [&](long long tt, float4 (&v)[4]) {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        long long e = e0 + (long long)(j * 32 + lane) * 4;
-        v[j] = (e < p.n) ? odtk_ld_stream_f4(reinterpret_cast<const float4 *>(s + e))
-                         : make_float4(p.thresh, p.thresh, p.thresh, p.thresh);
+        long long e = tt * kTile + (long long)(j * 32 + lane) * 4;
+        // out-of-range lanes get `thresh`: thresh > thresh is false, so they never pass
+        v[j] = (e < n) ? odtk_ld_stream_f4(reinterpret_cast<const float4 *>(s + e))
+                       : make_float4(thresh, thresh, thresh, thresh);
       }
+    };
+    float4 cur[4], nxt[4];
+    if (t < ntiles) load_tile(t, cur);
+    for (; t < ntiles; t += wstride) {
+      const bool more = (t + wstride) < ntiles;
+      if (more) load_tile(t + wstride, nxt);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        long long e = e0 + (long long)(j * 32 + lane) * 4;
-        // (e < n) is implied by the thresh fill: thresh > thresh is false
-        push(v[j].x > p.thresh, v[j].x, e + 0);
-        push(v[j].y > p.thresh, v[j].y, e + 1);
-        push(v[j].z > p.thresh, v[j].z, e + 2);
-        push(v[j].w > p.thresh, v[j].w, e + 3);
+        long long e = t * kTile + (long long)(j * 32 + lane) * 4;
+        push(cur[j].x > thresh, cur[j].x, e + 0);
+        push(cur[j].y > thresh, cur[j].y, e + 1);
+        push(cur[j].z > thresh, cur[j].z, e + 2);
+        push(cur[j].w > thresh, cur[j].w, e + 3);
       }
-    } else {
+      if (nstaged >= 32) flush();
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+      }
+    }
+  } else {
+    for (; t < ntiles; t += wstride) {
+      const long long e0 = t * kTile;
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         long long e = e0 + j * 32 + lane;
-        v[j] = (e < p.n) ? odtk_ld_stream_f1(s + e) : p.thresh;
+        v[j] = (e < n) ? odtk_ld_stream_f1(s + e) : thresh;
       }
 #pragma unroll
-      for (int j = 0; j < 16; j++) push(v[j] > p.thresh, v[j], e0 + j * 32 + lane);
+      for (int j = 0; j < 16; j++) push(v[j] > thresh, v[j], e0 + j * 32 + lane);
+      if (nstaged >= 32) flush();
     }
-    if (nstaged >= 32) flush();
   }
   flush();
 }
 
 // ------------------------------------------------------------------------------------
-struct SelectParams {
-  const float *scores;  // [B, n] dense scores (slow path + nothing else); may be NULL
-  const float *deltas;  // [B, A*NBOX, H, W]
-  long long n;
-  int height, width, scale, num_anchors, num_classes;
-  int has_anchors;
-  float thresh;
-  uint32_t key_thresh;
-  int shift;
-  int top_n;
-  const int *counts;
-  const uint32_t *hist;
-  const uint2 *cand;
-  long long cap;
-  float *out_scores, *out_boxes, *out_classes;
-  long long out_stride, out_offset;
-};
+// Histogram suffix scan by the whole CTA: highest bin b* with sum_{bin >= b*} >= top_n, and
+// that sum.  hist has kHistBins entries in shared memory; requires sum(hist) >= top_n.
+// scratch: s_w[32], s_res[2].
+__device__ __forceinline__ void find_bstar(const uint32_t *shist, int top_n, int *s_w, int *s_res,
+                                           int &bstar, int &nsel) {
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+  const int per = kHistBins / T;  // bins per thread, descending order
+  int own = 0;
+  for (int q = 0; q < per; q++) own += (int)shist[kHistBins - 1 - (t * per + q)];
+  int incl = own;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? s_w[lane] : 0, wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_w[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  incl += s_w[warp];
+  int acc = incl - own;
+  if (acc < top_n && incl >= top_n) {
+    for (int q = 0; q < per; q++) {
+      int b = kHistBins - 1 - (t * per + q);
+      acc += (int)shist[b];
+      if (acc >= top_n) { s_res[0] = b; s_res[1] = acc; break; }
+    }
+  }
+  __syncthreads();
+  bstar = s_res[0];
+  nsel = s_res[1];
+}
 
+// K2: grid = (kGatherSlices, L*B), block = 256.
+__global__ void __launch_bounds__(kGatherThreads) gather_top_kernel(const __grid_constant__ DecodeParams p) {
+  __shared__ uint32_t shist[kHistBins];
+  __shared__ int s_w[32];
+  __shared__ int s_res[2];
+  __shared__ int s_base;
+  const int slot = blockIdx.y, level = slot / p.batch, img = slot - level * p.batch;
+  const LevelDesc &L = p.lv[level];
+  const int total = p.counts[slot];
+  if (total <= p.top_n || (long long)total > L.cap) return;  // index mode / overflow: K3 handles it
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t *hist = p.hist + (long long)slot * kHistBins;
+  for (int i = t; i < kHistBins; i += kGatherThreads) shist[i] = hist[i];
+  __syncthreads();
+  int bstar, nsel;
+  find_bstar(shist, p.top_n, s_w, s_res, bstar, nsel);
+  if (nsel > kSortCap) return;  // tie bin too large: K3 runs the exact radix select
+  const uint2 *cand = p.cand + L.cand_off + (long long)img * L.cap;
+  unsigned long long *sel = p.sel + (long long)slot * kSortCap;
+  const int per_slice = (total + kGatherSlices - 1) / kGatherSlices;
+  const int j0 = blockIdx.x * per_slice;
+  const int j1 = min(total, j0 + per_slice);
+  constexpr int U = 8;
+  for (int jb = j0; jb < j1; jb += kGatherThreads * U) {
+    uint2 c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int j = jb + u * kGatherThreads + t;
+      c[u] = (j < j1) ? cand[j] : make_uint2(0u, 0u);
+    }
+    bool hit[U];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int j = jb + u * kGatherThreads + t;
+      hit[u] = (j < j1) && hist_bin(c[u].x, p.key_thresh, p.shift) >= bstar;
+      mine += hit[u];
+    }
+    // block-aggregated reservation: warp scan -> one global atomic per CTA per batch
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (t == 0) {
+      int acc = 0;
+      for (int w = 0; w < kGatherThreads / 32; w++) { int v = s_w[w]; s_w[w] = acc; acc += v; }
+      s_base = acc ? atomicAdd(p.selcount + slot, acc) : 0;
+    }
+    __syncthreads();
+    int pos = s_base + s_w[warp] + incl - mine;
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (hit[u]) { sel[pos++] = ((unsigned long long)c[u].x << 32) | (uint32_t)(~c[u].y); }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Block-wide radix select (8 passes x 8 bits, MSB first) of the `need`-th largest unique
 // 64-bit composite among the items produced by src(j) for j in [0, total).  Returns the
 // smallest composite that belongs to the top `need`.  Exact for any input; only used when
@@ -176,7 +303,7 @@ __device__ unsigned long long radix_select_kth(Src src, long long total, int nee
         acc += (int)sh256[d];
       }
       sh_misc[0] = d;
-      sh_misc[1] = need - acc;             // how many are still needed inside digit d
+      sh_misc[1] = need - acc;  // how many are still needed inside digit d
       sh_misc[2] = (int)sh256[d];
     }
     __syncthreads();
@@ -189,24 +316,24 @@ __device__ unsigned long long radix_select_kth(Src src, long long total, int nee
   return prefix;
 }
 
-// K2: grid = B, block = 1024.
+// K3: grid = L*B, block = 1024.
 template <int NBOX>
-__global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, AnchorTable anchors) {
+__global__ void __launch_bounds__(1024) select_decode_kernel(const __grid_constant__ DecodeParams p) {
   __shared__ unsigned long long skey[kSortCap];
   __shared__ uint32_t shist[kHistBins];
-  __shared__ int s_wsum[32];
+  __shared__ int s_w[32];
   __shared__ int s_misc[8];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int img = blockIdx.x;
-  const long long total = p.counts[img];
-  const uint2 *cand = p.cand + (long long)img * p.cap;
-  const float *dense = p.scores ? p.scores + (long long)img * p.n : nullptr;
+  const int t = threadIdx.x;
+  const int slot = blockIdx.x, level = slot / p.batch, img = slot - level * p.batch;
+  const LevelDesc &L = p.lv[level];
+  const long long total = p.counts[slot];
+  const uint2 *cand = p.cand + L.cand_off + (long long)img * L.cap;
+  const float *dense = L.scores + (long long)img * L.n;
 
   // composite in SCORE mode: (score key << 32) | ~index      -> score desc, index asc
   // composite in INDEX mode: (~index << 32) | score key       -> index asc
-  bool index_mode = total <= (long long)p.top_n;
+  const bool index_mode = total <= (long long)p.top_n;
   int nsel = 0;
-
   if (t == 0) s_misc[3] = 0;
   __syncthreads();
 
@@ -217,70 +344,32 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, Anc
       skey[j] = ((unsigned long long)(~c.y) << 32) | c.x;
     }
   } else {
-    bool slow = total > p.cap;
-    int bstar = 0;
+    bool slow = total > L.cap;
     if (!slow) {
-      // histogram suffix scan: find the highest bin b* with sum_{bin >= b*} >= top_n
-      const uint32_t *hist = p.hist + (long long)img * kHistBins;
+      const uint32_t *hist = p.hist + (long long)slot * kHistBins;
       for (int i = t; i < kHistBins; i += blockDim.x) shist[i] = hist[i];
       __syncthreads();
-      // thread t owns bins (kHistBins-1-2t, kHistBins-2-2t): descending order
-      int b0 = kHistBins - 1 - 2 * t, b1 = b0 - 1;
-      int c0 = (int)shist[b0], c1 = (int)shist[b1];
-      int own = c0 + c1, incl = own;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s_wsum[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        int w = s_wsum[lane], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int v = __shfl_up_sync(0xffffffffu, wi, o);
-          if (lane >= o) wi += v;
-        }
-        s_wsum[lane] = wi - w;  // exclusive
-      }
-      __syncthreads();
-      incl += s_wsum[warp];
-      int excl = incl - own;
-      if (excl < p.top_n && incl >= p.top_n) {
-        if (excl + c0 >= p.top_n) { s_misc[0] = b0; s_misc[1] = excl + c0; }
-        else                      { s_misc[0] = b1; s_misc[1] = incl; }
-      }
-      __syncthreads();
-      bstar = s_misc[0];
-      nsel = s_misc[1];
+      int bstar;
+      find_bstar(shist, p.top_n, s_w, s_misc, bstar, nsel);
       if (nsel > kSortCap) slow = true;
     }
     if (!slow) {
-      const int cnt = (int)total;
-      for (int j = t; j < cnt; j += blockDim.x) {
-        uint2 c = cand[j];
-        if (hist_bin(c.x, p.key_thresh, p.shift) >= bstar) {
-          int pos = atomicAdd(&s_misc[3], 1);
-          skey[pos] = ((unsigned long long)c.x << 32) | (uint32_t)(~c.y);
-        }
-      }
-      __syncthreads();
-      nsel = s_misc[3];
+      // K2 gathered exactly the candidates of bins >= b*
+      const unsigned long long *sel = p.sel + (long long)slot * kSortCap;
+      for (int j = t; j < nsel; j += blockDim.x) skey[j] = sel[j];
     } else {
-      // exact slow path: radix select on the composite key
       unsigned long long kth;
       const float thresh = p.thresh;
-      if (total > p.cap) {
-        if (dense == nullptr) { __trap(); }
+      __syncthreads();
+      if (total > L.cap) {  // candidate list overflowed: go back to the dense scores
         auto src = [=](long long j, unsigned long long &c) {
           float v = dense[j];
           if (!(v > thresh)) return false;
           c = ((unsigned long long)odtk_float_key(v) << 32) | (uint32_t)(~(uint32_t)j);
           return true;
         };
-        kth = radix_select_kth(src, p.n, p.top_n, shist, s_misc);
-        for (long long j = t; j < p.n; j += blockDim.x) {
+        kth = radix_select_kth(src, L.n, p.top_n, shist, s_misc);
+        for (long long j = t; j < L.n; j += blockDim.x) {
           unsigned long long c;
           if (src(j, c) && c >= kth) skey[atomicAdd(&s_misc[3], 1)] = c;
         }
@@ -309,11 +398,13 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, Anc
 
   // decode: reference decode.cu:119-159 / decode_rotate.cu:115-166
   const int n_out = nsel < p.top_n ? nsel : p.top_n;
-  const int H = p.height, W = p.width, A = p.num_anchors, C = p.num_classes;
-  const float *d = p.deltas + (long long)img * ((long long)A * NBOX * H * W);
-  float *os = p.out_scores + (long long)img * p.out_stride + p.out_offset;
-  float *ob = p.out_boxes + ((long long)img * p.out_stride + p.out_offset) * NBOX;
-  float *oc = p.out_classes + (long long)img * p.out_stride + p.out_offset;
+  const int H = L.height, W = L.width, A = p.num_anchors, C = p.num_classes;
+  const float *d = L.deltas + (long long)img * ((long long)A * NBOX * H * W);
+  const long long obase = (long long)img * p.out_stride + L.out_offset;
+  float *os = p.out_scores + obase;
+  float *ob = p.out_boxes + obase * NBOX;
+  float *oc = p.out_classes + obase;
+  const float *anchors = p.anchors[level];
   for (int k = t; k < p.top_n; k += blockDim.x) {
     if (k < n_out) {
       unsigned long long c = skey[k];
@@ -327,9 +418,9 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, Anc
 #pragma unroll
       for (int q = 0; q < NBOX; q++) box[q] = d[((long long)(a * NBOX + q) * H + y) * W + x];
       if (p.has_anchors) {
-        float fx = (float)((long long)x * p.scale);
-        float fy = (float)((long long)y * p.scale);
-        const float *an = anchors.v + 4 * a;
+        float fx = (float)((long long)x * L.scale);
+        float fy = (float)((long long)y * L.scale);
+        const float *an = anchors + 4 * a;
         float x1 = fx + an[0];
         float y1 = fy + an[1];
         float x2 = fx + an[2];
@@ -342,8 +433,8 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, Anc
         float pred_h = expf(box[3]) * h;
         box[0] = fmaxf(0.0f, pred_ctr_x - 0.5f * pred_w);
         box[1] = fmaxf(0.0f, pred_ctr_y - 0.5f * pred_h);
-        box[2] = fminf(pred_ctr_x + 0.5f * pred_w - 1.0f, (float)((long long)W * p.scale) - 1.0f);
-        box[3] = fminf(pred_ctr_y + 0.5f * pred_h - 1.0f, (float)((long long)H * p.scale) - 1.0f);
+        box[2] = fminf(pred_ctr_x + 0.5f * pred_w - 1.0f, (float)((long long)W * L.scale) - 1.0f);
+        box[3] = fminf(pred_ctr_y + 0.5f * pred_h - 1.0f, (float)((long long)H * L.scale) - 1.0f);
       }
       os[k] = odtk_key_float(key);
 #pragma unroll
@@ -358,21 +449,14 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(SelectParams p, Anc
   }
 }
 
-// workspace layout: counts | hist | cand
+// workspace layout: counts | selcount | hist | sel | cand(level 0) | cand(level 1) ...
 struct DecodeWs {
-  size_t counts_off, hist_off, cand_off, total;
-  long long cap;
+  size_t counts_off, selcount_off, hist_off, zero_bytes, sel_off, cand_off, total;
 };
-DecodeWs decode_ws_layout(int batch, long long n, int top_n) {
-  DecodeWs w;
+
+long long level_cap(long long n, int top_n) {
   long long cap = n < (1ll << 20) ? n : (1ll << 20);
-  if (cap < top_n) cap = top_n;
-  w.cap = cap;
-  w.counts_off = 0;
-  w.hist_off = odtk_align_up((size_t)batch * sizeof(int));
-  w.cand_off = w.hist_off + odtk_align_up((size_t)batch * kHistBins * sizeof(uint32_t));
-  w.total = w.cand_off + odtk_align_up((size_t)batch * (size_t)cap * sizeof(uint2));
-  return w;
+  return cap < top_n ? top_n : cap;
 }
 
 int choose_shift(uint32_t key_thresh) {
@@ -386,80 +470,129 @@ int choose_shift(uint32_t key_thresh) {
 
 }  // namespace
 
+extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_level_t *levels,
+                                        size_t num_anchors, size_t num_classes, size_t num_anchor_floats,
+                                        float score_thresh, int top_n, int nbox, void *const *outputs,
+                                        size_t out_stride, size_t out_offset, void *workspace,
+                                        size_t workspace_size, odtk_stream_t stream_) {
+  if (batch <= 0 || num_levels <= 0 || !levels || num_anchors == 0 || num_classes == 0 || top_n <= 0)
+    return ODTK_E_INVALID;
+  if (nbox != 4 && nbox != 6) return ODTK_E_INVALID;
+  if (num_levels > kMaxLevels || top_n > ODTK_MAX_TOP_N || num_anchors > (size_t)kMaxAnchors)
+    return ODTK_E_UNSUPPORTED;
+  if (num_anchor_floats != 0 && num_anchor_floats != 4 * num_anchors) return ODTK_E_INVALID;
+  static DecodeParams P;  // large: keep it off the stack (host-side staging only)
+  DecodeParams &p = P;
+  const int slots = num_levels * batch;
+  long long cand_entries = 0, total_n = 0;
+  for (int l = 0; l < num_levels; l++) {
+    if (levels[l].height == 0 || levels[l].width == 0) return ODTK_E_INVALID;
+    long long n = (long long)num_anchors * num_classes * levels[l].height * levels[l].width;
+    if (n >= (1ll << 31)) return ODTK_E_UNSUPPORTED;  // flat index is int32 (decode.cu:122)
+    p.lv[l].n = n;
+    p.lv[l].cap = level_cap(n, top_n);
+    p.lv[l].cand_off = cand_entries;
+    cand_entries += p.lv[l].cap * batch;
+    total_n += n;
+  }
+  DecodeWs ws;
+  ws.counts_off = 0;
+  ws.selcount_off = odtk_align_up((size_t)slots * sizeof(int));
+  ws.hist_off = ws.selcount_off + odtk_align_up((size_t)slots * sizeof(int));
+  ws.zero_bytes = ws.hist_off + odtk_align_up((size_t)slots * kHistBins * sizeof(uint32_t));
+  ws.sel_off = ws.zero_bytes;
+  ws.cand_off = ws.sel_off + odtk_align_up((size_t)slots * kSortCap * sizeof(unsigned long long));
+  ws.total = ws.cand_off + odtk_align_up((size_t)cand_entries * sizeof(uint2));
+  if (!workspace || !workspace_size) return (long long)ws.total;
+  if (workspace_size < ws.total) return ODTK_E_WORKSPACE;
+  if (!outputs || !outputs[0] || !outputs[1] || !outputs[2]) return ODTK_E_INVALID;
+  if (out_stride < out_offset + (size_t)top_n * num_levels) return ODTK_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char *base = (char *)workspace;
+
+  // filter grid: one wave of resident CTAs (55 registers x 256 threads -> 4 per SM) x 148 SMs,
+  // split between levels by bytes.  ODTK_FILTER_CTAS_PER_SM overrides (tuning knob).
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    const char *e = getenv("ODTK_FILTER_CTAS_PER_SM");
+    ctas_per_sm = e ? atoi(e) : 4;
+    if (ctas_per_sm < 1) ctas_per_sm = 4;
+  }
+  const long long budget = 148ll * ctas_per_sm;
+  int blk = 0;
+  for (int l = 0; l < num_levels; l++) {
+    LevelDesc &L = p.lv[l];
+    if (!levels[l].scores || !levels[l].deltas) return ODTK_E_INVALID;
+    if (num_anchor_floats && !levels[l].anchors) return ODTK_E_INVALID;
+    L.scores = (const float *)levels[l].scores;
+    L.deltas = (const float *)levels[l].deltas;
+    L.height = (int)levels[l].height;
+    L.width = (int)levels[l].width;
+    L.scale = (int)levels[l].scale;
+    L.out_offset = (int)(out_offset + (size_t)l * top_n);
+    long long ntiles = (L.n + kTile - 1) / kTile;
+    long long want = (budget * L.n + total_n * batch - 1) / (total_n * batch);
+    long long maxb = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (want > maxb) want = maxb;
+    if (want < 1) want = 1;
+    L.blk_per_img = (int)want;
+    L.blk_begin = blk;
+    blk += L.blk_per_img * batch;
+    L.vec = (L.n % 4 == 0) && (((uintptr_t)L.scores) % 16 == 0);
+    L.pad = 0;
+    for (size_t i = 0; i < 4 * (size_t)kMaxAnchors; i++)
+      p.anchors[l][i] = i < num_anchor_floats ? levels[l].anchors[i] : 0.0f;
+  }
+  p.num_levels = num_levels;
+  p.batch = batch;
+  p.num_anchors = (int)num_anchors;
+  p.num_classes = (int)num_classes;
+  p.has_anchors = num_anchor_floats != 0;
+  p.top_n = top_n;
+  p.thresh = score_thresh;
+  p.key_thresh = odtk_float_key(score_thresh);
+  p.shift = choose_shift(p.key_thresh);
+  p.counts = (int *)(base + ws.counts_off);
+  p.selcount = (int *)(base + ws.selcount_off);
+  p.hist = (uint32_t *)(base + ws.hist_off);
+  p.sel = (unsigned long long *)(base + ws.sel_off);
+  p.cand = (uint2 *)(base + ws.cand_off);
+  p.out_scores = (float *)outputs[0];
+  p.out_boxes = (float *)outputs[1];
+  p.out_classes = (float *)outputs[2];
+  p.out_stride = (long long)out_stride;
+
+  if (cudaMemsetAsync(base, 0, ws.zero_bytes, stream) != cudaSuccess) return ODTK_E_CUDA;
+  {
+    OdtkProfScope prof(ODTK_PROF_FILTER, stream);
+    score_filter_kernel<<<blk, kFilterThreads, 0, stream>>>(p);
+  }
+  {
+    OdtkProfScope prof(ODTK_PROF_SELECT, stream);
+    gather_top_kernel<<<dim3(kGatherSlices, slots), kGatherThreads, 0, stream>>>(p);
+    if (nbox == 4) select_decode_kernel<4><<<slots, 1024, 0, stream>>>(p);
+    else           select_decode_kernel<6><<<slots, 1024, 0, stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
 extern "C" long long odtk_decode_ex(int batch, const void *const *inputs, void *const *outputs,
                                     size_t height, size_t width, size_t scale, size_t num_anchors,
                                     size_t num_classes, const float *anchors, size_t num_anchor_floats,
                                     float score_thresh, int top_n, int nbox, size_t out_stride,
                                     size_t out_offset, void *workspace, size_t workspace_size,
-                                    odtk_stream_t stream_) {
-  if (batch <= 0 || height == 0 || width == 0 || num_anchors == 0 || num_classes == 0 || top_n <= 0)
-    return ODTK_E_INVALID;
-  if (nbox != 4 && nbox != 6) return ODTK_E_INVALID;
-  if (top_n > ODTK_MAX_TOP_N || num_anchors > (size_t)kMaxAnchors) return ODTK_E_UNSUPPORTED;
-  if (num_anchor_floats != 0 && num_anchor_floats != 4 * num_anchors) return ODTK_E_INVALID;
-  const long long n = (long long)num_anchors * num_classes * height * width;
-  if (n >= (1ll << 31)) return ODTK_E_UNSUPPORTED;  // flat index is int32 (decode.cu:122)
-  DecodeWs ws = decode_ws_layout(batch, n, top_n);
-  if (!workspace || !workspace_size) return (long long)ws.total;
-  if (workspace_size < ws.total) return ODTK_E_WORKSPACE;
-  if (!inputs || !outputs || !inputs[0] || !inputs[1] || !outputs[0] || !outputs[1] || !outputs[2])
-    return ODTK_E_INVALID;
-  if (num_anchor_floats && !anchors) return ODTK_E_INVALID;
-  if (out_stride < out_offset + (size_t)top_n) return ODTK_E_INVALID;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  char *base = (char *)workspace;
-
-  FilterParams fp;
-  fp.scores = (const float *)inputs[0];
-  fp.n = n;
-  fp.thresh = score_thresh;
-  fp.key_thresh = odtk_float_key(score_thresh);
-  fp.shift = choose_shift(fp.key_thresh);
-  fp.counts = (int *)(base + ws.counts_off);
-  fp.hist = (uint32_t *)(base + ws.hist_off);
-  fp.cand = (uint2 *)(base + ws.cand_off);
-  fp.cap = ws.cap;
-  if (cudaMemsetAsync(base, 0, ws.cand_off, stream) != cudaSuccess) return ODTK_E_CUDA;
-
-  const long long ntiles = (n + kTile - 1) / kTile;
-  long long blocks = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  // 6 resident CTAs per SM (34.8 KB of staging each) x 148 SMs, shared by the batch
-  long long max_blocks = (148ll * 6 + batch - 1) / batch;
-  if (max_blocks < 1) max_blocks = 1;
-  if (blocks > max_blocks) blocks = max_blocks;
-  dim3 grid((unsigned)blocks, (unsigned)batch);
-  const bool vec = (n % 4 == 0) && (((uintptr_t)inputs[0]) % 16 == 0);
-  {
-    OdtkProfScope prof(ODTK_PROF_FILTER, stream);
-    if (vec) score_filter_kernel<true><<<grid, kFilterThreads, 0, stream>>>(fp);
-    else     score_filter_kernel<false><<<grid, kFilterThreads, 0, stream>>>(fp);
-  }
-
-  SelectParams sp;
-  sp.scores = fp.scores;
-  sp.deltas = (const float *)inputs[1];
-  sp.n = n;
-  sp.height = (int)height; sp.width = (int)width; sp.scale = (int)scale;
-  sp.num_anchors = (int)num_anchors; sp.num_classes = (int)num_classes;
-  sp.has_anchors = num_anchor_floats != 0;
-  sp.thresh = score_thresh;
-  sp.key_thresh = fp.key_thresh;
-  sp.shift = fp.shift;
-  sp.top_n = top_n;
-  sp.counts = fp.counts; sp.hist = fp.hist; sp.cand = fp.cand; sp.cap = ws.cap;
-  sp.out_scores = (float *)outputs[0];
-  sp.out_boxes = (float *)outputs[1];
-  sp.out_classes = (float *)outputs[2];
-  sp.out_stride = (long long)out_stride;
-  sp.out_offset = (long long)out_offset;
-  AnchorTable at;
-  for (size_t i = 0; i < 4 * (size_t)kMaxAnchors; i++) at.v[i] = i < num_anchor_floats ? anchors[i] : 0.0f;
-  {
-    OdtkProfScope prof(ODTK_PROF_SELECT, stream);
-    if (nbox == 4) select_decode_kernel<4><<<batch, 1024, 0, stream>>>(sp, at);
-    else           select_decode_kernel<6><<<batch, 1024, 0, stream>>>(sp, at);
-  }
-  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+                                    odtk_stream_t stream) {
+  odtk_level_t lv;
+  const bool query = !workspace || !workspace_size;
+  if (!query && (!inputs || !inputs[0] || !inputs[1])) return ODTK_E_INVALID;
+  lv.scores = query ? nullptr : inputs[0];
+  lv.deltas = query ? nullptr : inputs[1];
+  lv.height = height;
+  lv.width = width;
+  lv.scale = scale;
+  lv.anchors = anchors;
+  return odtk_decode_levels(batch, 1, &lv, num_anchors, num_classes, num_anchor_floats, score_thresh, top_n,
+                            nbox, outputs, out_stride, out_offset, workspace, workspace_size, stream);
 }
 
 extern "C" long long odtk_decode(int batch, const void *const *inputs, void *const *outputs, size_t height,

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_kept[kMaxDet];
   __shared__ int s_tail[kMaxDet];
-  __shared__ int s_next[3];
+  __shared__ unsigned s_alive[kMaxCount / 32];
   __shared__ int s_wsum[32];
   __shared__ int s_n;
 
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   // ---- 1. keys + sort (nms.cu:125-137) ------------------------------------------------
   unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
   const int P = odtk_next_pow2(count);
-  if (t == 0) { s_n = 0; s_next[0] = s_next[1] = s_next[2] = INT_MAX; }
+  if (t == 0) s_n = 0;
   __syncthreads();
   int nvalid = 0;
   for (int i = t; i < P; i += kThreads) {
@@ -245,43 +245,53 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   __syncthreads();
 
   // ---- 3. greedy over keepers (nms_kernel, nms.cu:49-79) ---------------------------------
+  // Survivor bits live twice: privately (each thread owns ranks t + k*1024) to skip dead
+  // ranks, and as a shared bitmap that every thread scans for the next keeper after the
+  // barrier.  A thread that races ahead only clears bits ABOVE the next keeper, so a slower
+  // thread still finds the same one: one barrier per keeper, no atomics on a hot word.
   unsigned alive = 0;  // bit k: rank t + k*1024 not suppressed
+  int my_cls[kMaxRanks];
 #pragma unroll
-  for (int k = 0; k < kMaxRanks; k++)
-    if (t + k * kThreads < n) alive |= 1u << k;
+  for (int k = 0; k < kMaxRanks; k++) {
+    int r = t + k * kThreads;
+    my_cls[k] = (r < n) ? scls[r] : -1;
+    if (r < n) alive |= 1u << k;
+  }
+  const int nwords = (n + 31) >> 5;
+  for (int w = t; w < nwords; w += kThreads) {
+    int rem = n - (w << 5);
+    s_alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+  }
+  __syncthreads();
   const int nd = n < D ? n : D;
-  int kept = 0, m = (n > 0) ? 0 : INT_MAX, iter = 0;
+  int kept = 0, m = (n > 0) ? 0 : INT_MAX;
   while (m < n) {
     if (t == 0) s_kept[kept] = m;
     kept++;
     if (kept >= D) break;
-    if (t == 0) s_next[(iter + 1) % 3] = INT_MAX;
     float mb[NBOX];
 #pragma unroll
     for (int q = 0; q < NBOX; q++) mb[q] = sbox[m * NBOX + q];
     const int mcls = scls[m];
-    int first = INT_MAX;
 #pragma unroll
     for (int k = 0; k < kMaxRanks; k++) {
       int r = t + k * kThreads;
-      if (r > m && ((alive >> k) & 1u)) {
-        bool sup = false;
-        if (scls[r] == mcls) {
-          float ib[NBOX];
+      if (r > m && ((alive >> k) & 1u) && my_cls[k] == mcls) {
+        float ib[NBOX];
 #pragma unroll
-          for (int q = 0; q < NBOX; q++) ib[q] = sbox[r * NBOX + q];
-          float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
-          sup = ov > p.thresh;
+        for (int q = 0; q < NBOX; q++) ib[q] = sbox[r * NBOX + q];
+        float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
+        if (ov > p.thresh) {
+          alive &= ~(1u << k);
+          atomicAnd(&s_alive[r >> 5], ~(1u << (r & 31)));
         }
-        if (sup) alive &= ~(1u << k);
-        else if (r < first) first = r;
       }
     }
-    first = __reduce_min_sync(0xffffffffu, first);
-    if (lane == 0 && first != INT_MAX) atomicMin(&s_next[iter % 3], first);
     __syncthreads();
-    m = s_next[iter % 3];
-    iter++;
+    int w = (m + 1) >> 5;
+    unsigned bits = (w < nwords) ? (s_alive[w] & (0xffffffffu << ((m + 1) & 31))) : 0u;
+    while (bits == 0u && ++w < nwords) bits = s_alive[w];
+    m = bits ? ((w << 5) + __ffs(bits) - 1) : INT_MAX;
   }
   __syncthreads();
 

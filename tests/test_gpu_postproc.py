@@ -202,6 +202,13 @@ def test_decode_then_nms_full_pipeline_batch2():
             np.testing.assert_allclose(outs_g[-1][1].cpu().numpy(), o[1], atol=1e-3, rtol=0)
     cat = [torch.cat(t, 1) for t in zip(*outs_g)]
     assert cat[0].shape == (2, 5000)
+    # the all-levels entry point (3 launches) must equal the torch.cat of the per-level calls
+    all_anchors = [oracle.generate_anchors(s, oracle.DEFAULT_RATIOS, oracle.DEFAULT_SCALES).reshape(-1).tolist()
+                   for s in synth.LEVEL_STRIDES]
+    fused = _C.decode_levels([c.to(DEV) for c in cls], [d.to(DEV) for d in deltas], all_anchors,
+                             synth.LEVEL_STRIDES, 0.05, 1000)
+    for f, c in zip(fused, cat):
+        np.testing.assert_array_equal(f.cpu().numpy(), c.cpu().numpy())
     gs, gb, gc, gi = [t.cpu().numpy() for t in _C.nms(*cat, 0.5, 100, False, return_index=True)]
     os_, ob, oc, oi = oracle.nms(cat[0].cpu().numpy(), cat[1].cpu().numpy(), cat[2].cpu().numpy(), 0.5, 100, return_index=True)
     np.testing.assert_array_equal(gi, oi)
