@@ -515,8 +515,8 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     const char *e = getenv("ODTK_FILTER_CTAS_PER_SM");
-    ctas_per_sm = e ? atoi(e) : 4;
-    if (ctas_per_sm < 1) ctas_per_sm = 4;
+    ctas_per_sm = e ? atoi(e) : 12;  // measured on B200: 4 -> 3.7, 6 -> 4.67, 12 -> 4.79 TB/s
+    if (ctas_per_sm < 1) ctas_per_sm = 12;
   }
   const long long budget = 148ll * ctas_per_sm;
   int blk = 0;

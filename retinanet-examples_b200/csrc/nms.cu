@@ -7,22 +7,26 @@
 // __syncthreads each -> second radix sort -> gathers.  Here the whole batch is one launch,
 // one CTA per image, nothing leaves shared memory:
 //
-//   1. composite keys (score key << 32 | ~position) for scores > 0, bitonic network in
-//      shared memory == the reference's stable descending radix sort;
-//   2. boxes / classes gathered once into shared memory in rank order;
-//   3. greedy loop over KEEPERS only (the reference loops over every candidate): each
-//      iteration broadcasts the keeper, all threads test their own ranks (class gate
-//      first, IEEE division, +1 widths), and a warp-reduced atomicMin finds the next
-//      survivor.  The loop stops at detections_per_im keepers -- exact, because the output
-//      is the first D entries of (kept..., suppressed...) and later candidates can never
-//      change earlier decisions (SURVEY.md section 8 note N1);
-//   4. if fewer than D were kept the tail is the first suppressed candidates in rank order
+//   1. unique composite keys (score key << 13 | ~position) for scores > 0, one block-wide
+//      cub radix sort (45 bits) == the reference's stable descending device radix sort;
+//   2. the ranks are walked in windows of 1024 (one rank per thread): a window is first
+//      pruned against the keepers of earlier windows, then a greedy loop runs over its
+//      KEEPERS only (the reference loops over every candidate): each iteration broadcasts the
+//      keeper from shared memory, every thread tests its own rank (class gate first, IEEE
+//      division, +1 widths) and clears its bit in a 32-word survivor bitmap that all threads
+//      scan for the next keeper.  The walk stops at detections_per_im keepers -- exact,
+//      because the output is the first D entries of (kept..., suppressed...) and later
+//      candidates never change earlier decisions (SURVEY.md section 8 note N1); with the
+//      BASELINE workload only the first window is ever touched;
+//   3. if fewer than D were kept the tail is the first suppressed candidates in rank order
 //      with score 0 and their boxes/classes, exactly what the reference's second sort
 //      leaves there (nms.cu:146-156).
 //
 // Arithmetic: fp32, IEEE division, no FMA contraction (-fmad=false): the PyTorch path is
 // the parity target, not the reference's --use_fast_math build.
 #include <limits.h>
+
+#include <cub/block/block_radix_sort.cuh>
 
 #include "common.cuh"
 #include "prof.cuh"
@@ -164,23 +168,32 @@ struct NmsParams {
   int fixed_angle;
 };
 
-// dynamic shared memory carve-up (bytes); the sort buffer is aliased by the gathered data
+constexpr int kPosBits = 13;  // count <= 6144 < 2^13
+typedef cub::BlockRadixSort<unsigned long long, kThreads, kMaxRanks> BlockSort;
+
+// Shared memory: the radix-sort scratch is dead once the ranks sit in registers, so the
+// per-window and keeper arrays alias it.
 template <int NBOX>
 struct NmsSmem {
-  static constexpr size_t box_bytes(int n) { return (size_t)n * NBOX * sizeof(float); }
-  static size_t total(int count) {
-    size_t sort_b = (size_t)odtk_next_pow2(count) * 8;
-    size_t data_b = box_bytes(count) + (size_t)count * 4 /*cls*/ + (size_t)count * 4 /*idx*/;
-    return (sort_b > data_b ? sort_b : data_b) + 16;
-  }
+  struct Data {
+    float wbox[kThreads][NBOX];   // current window, by window-local rank
+    int wcls[kThreads];
+    float kbox[kMaxDet][NBOX];    // keepers so far
+    int kcls[kMaxDet];
+    int kidx[kMaxDet];
+    int tidx[kMaxDet];            // suppressed candidates in rank order (output tail)
+  };
+  union U {
+    typename BlockSort::TempStorage sort;
+    Data d;
+  };
 };
 
 template <int NBOX>
 __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_kept[kMaxDet];
-  __shared__ int s_tail[kMaxDet];
-  __shared__ unsigned s_alive[kMaxCount / 32];
+  typename NmsSmem<NBOX>::U &sm = *reinterpret_cast<typename NmsSmem<NBOX>::U *>(smem_raw);
+  __shared__ unsigned s_alive[kThreads / 32];
   __shared__ int s_wsum[32];
   __shared__ int s_n;
 
@@ -191,148 +204,148 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   const float *bx = p.boxes + (long long)img * count * NBOX;
   const float *cl = p.classes + (long long)img * count;
 
-  // ---- 1. keys + sort (nms.cu:125-137) ------------------------------------------------
-  unsigned long long *skey = reinterpret_cast<unsigned long long *>(smem_raw);
-  const int P = odtk_next_pow2(count);
+  // ---- 1. keys + stable descending sort (nms.cu:125-137) ---------------------------------
+  // composite = (score key << 13) | ~position: unique, so the radix sort reproduces cub's
+  // stable order of the reference.  Output is striped: thread t holds ranks t + k*1024.
   if (t == 0) s_n = 0;
   __syncthreads();
+  unsigned long long keys[kMaxRanks];
   int nvalid = 0;
-  for (int i = t; i < P; i += kThreads) {
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; k++) {
+    int i = t * kMaxRanks + k;  // blocked arrangement in, striped out
     unsigned long long c = 0ull;
     if (i < count) {
       float v = sc[i];
-      if (v > 0.0f) { c = ((unsigned long long)odtk_float_key(v) << 32) | (uint32_t)(~(uint32_t)i); nvalid++; }
+      if (v > 0.0f) {
+        c = ((unsigned long long)odtk_float_key(v) << kPosBits) | (unsigned)((~(unsigned)i) & ((1u << kPosBits) - 1u));
+        nvalid++;
+      }
     }
-    skey[i] = c;
+    keys[k] = c;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
   if (lane == 0 && nvalid) atomicAdd(&s_n, nvalid);
-  __syncthreads();
+  BlockSort(sm.sort).SortDescendingBlockedToStriped(keys, 0, 32 + kPosBits);
+  __syncthreads();  // sort scratch is dead; s_n is complete
   const int n = s_n;
-  odtk_bitonic_desc_u64(skey, P);
+  const int nd = n < D ? n : D;
 
-  // ---- 2. gather in rank order -----------------------------------------------------------
-  int my_idx[kMaxRanks];
+  // ---- 2. windows of 1024 ranks: prune against the keepers so far, then greedy ---------
+  int kept = 0, ntail = 0;
+  const int nwin = (n + kThreads - 1) / kThreads;
+#pragma unroll 1
+  for (int w = 0; w < nwin && kept < D; w++) {
+    const int r = t + w * kThreads;
+    const bool valid = r < n;
+    // select keys[w] without dynamic register indexing
+    unsigned long long key = 0ull;
 #pragma unroll
-  for (int k = 0; k < kMaxRanks; k++) {
-    int r = t + k * kThreads;
-    my_idx[k] = (r < n) ? (int)(~(uint32_t)skey[r]) : -1;
-  }
-  __syncthreads();  // the sort buffer is dead from here on
-  float *sbox = reinterpret_cast<float *>(smem_raw);
-  int *scls = reinterpret_cast<int *>(smem_raw + (size_t)count * NBOX * sizeof(float));
-  int *sidx = scls + count;
-#pragma unroll
-  for (int k = 0; k < kMaxRanks; k++) {
-    int r = t + k * kThreads;
-    if (r < n) {
-      int i = my_idx[k];
+    for (int k = 0; k < kMaxRanks; k++)
+      if (k == w) key = keys[k];
+    const int idx = valid ? (int)((~(unsigned)key) & ((1u << kPosBits) - 1u)) : 0;
+    float ib[NBOX];
+    int icls = -1;
+    if (valid) {
       if (NBOX == 4) {
-        float4 b = *reinterpret_cast<const float4 *>(bx + (long long)i * 4);
-        *reinterpret_cast<float4 *>(sbox + r * 4) = b;
+        float4 b = *reinterpret_cast<const float4 *>(bx + (long long)idx * 4);
+        ib[0] = b.x; ib[1] = b.y; ib[2] = b.z; ib[3] = b.w;
       } else {
 #pragma unroll
         for (int q = 0; q < NBOX; q += 2) {
-          float2 b = *reinterpret_cast<const float2 *>(bx + (long long)i * NBOX + q);
-          *reinterpret_cast<float2 *>(sbox + r * NBOX + q) = b;
+          float2 b = *reinterpret_cast<const float2 *>(bx + (long long)idx * NBOX + q);
+          ib[q] = b.x; ib[q + 1] = b.y;
         }
       }
-      scls[r] = (int)cl[i];  // float -> int cast as nms.cu:55-56
-      sidx[r] = i;
+      icls = (int)cl[idx];  // float -> int cast as nms.cu:55-56
+    } else {
+#pragma unroll
+      for (int q = 0; q < NBOX; q++) ib[q] = 0.0f;
     }
-  }
-  __syncthreads();
+    bool alive = valid;
+    if (w > 0 && alive) {  // suppression by keepers of earlier windows
+      for (int q = 0; q < kept; q++) {
+        if (sm.d.kcls[q] == icls) {
+          float mb[NBOX];
+#pragma unroll
+          for (int c = 0; c < NBOX; c++) mb[c] = sm.d.kbox[q][c];
+          float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
+          if (ov > p.thresh) { alive = false; break; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NBOX; q++) sm.d.wbox[t][q] = ib[q];
+    sm.d.wcls[t] = icls;
+    unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) s_alive[warp] = bal;
+    __syncthreads();
 
-  // ---- 3. greedy over keepers (nms_kernel, nms.cu:49-79) ---------------------------------
-  // Survivor bits live twice: privately (each thread owns ranks t + k*1024) to skip dead
-  // ranks, and as a shared bitmap that every thread scans for the next keeper after the
-  // barrier.  A thread that races ahead only clears bits ABOVE the next keeper, so a slower
-  // thread still finds the same one: one barrier per keeper, no atomics on a hot word.
-  unsigned alive = 0;  // bit k: rank t + k*1024 not suppressed
-  int my_cls[kMaxRanks];
+    // greedy over the keepers of this window (nms_kernel, nms.cu:49-79).  Every thread scans
+    // the 32-word survivor bitmap for the next keeper after the barrier; a thread that races
+    // ahead only clears bits ABOVE that keeper, so all threads agree without a second barrier.
+    int m = -1;
+    while (true) {
+      int ww = (m + 1) >> 5;
+      unsigned bits = (ww < 32) ? (s_alive[ww] & (0xffffffffu << ((m + 1) & 31))) : 0u;
+      while (bits == 0u && ++ww < 32) bits = s_alive[ww];
+      if (bits == 0u) break;
+      m = (ww << 5) + __ffs(bits) - 1;
+      if (t == m) {  // the keeper records itself
 #pragma unroll
-  for (int k = 0; k < kMaxRanks; k++) {
-    int r = t + k * kThreads;
-    my_cls[k] = (r < n) ? scls[r] : -1;
-    if (r < n) alive |= 1u << k;
-  }
-  const int nwords = (n + 31) >> 5;
-  for (int w = t; w < nwords; w += kThreads) {
-    int rem = n - (w << 5);
-    s_alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-  }
-  __syncthreads();
-  const int nd = n < D ? n : D;
-  int kept = 0, m = (n > 0) ? 0 : INT_MAX;
-  while (m < n) {
-    if (t == 0) s_kept[kept] = m;
-    kept++;
-    if (kept >= D) break;
-    float mb[NBOX];
+        for (int q = 0; q < NBOX; q++) sm.d.kbox[kept][q] = ib[q];
+        sm.d.kcls[kept] = icls;
+        sm.d.kidx[kept] = idx;
+      }
+      kept++;
+      if (kept >= D) break;
+      if (alive && t > m && sm.d.wcls[m] == icls) {
+        float mb[NBOX];
 #pragma unroll
-    for (int q = 0; q < NBOX; q++) mb[q] = sbox[m * NBOX + q];
-    const int mcls = scls[m];
-#pragma unroll
-    for (int k = 0; k < kMaxRanks; k++) {
-      int r = t + k * kThreads;
-      if (r > m && ((alive >> k) & 1u) && my_cls[k] == mcls) {
-        float ib[NBOX];
-#pragma unroll
-        for (int q = 0; q < NBOX; q++) ib[q] = sbox[r * NBOX + q];
+        for (int q = 0; q < NBOX; q++) mb[q] = sm.d.wbox[m][q];
         float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
         if (ov > p.thresh) {
-          alive &= ~(1u << k);
-          atomicAnd(&s_alive[r >> 5], ~(1u << (r & 31)));
+          alive = false;
+          atomicAnd(&s_alive[warp], ~(1u << lane));
         }
       }
+      __syncthreads();
     }
     __syncthreads();
-    int w = (m + 1) >> 5;
-    unsigned bits = (w < nwords) ? (s_alive[w] & (0xffffffffu << ((m + 1) & 31))) : 0u;
-    while (bits == 0u && ++w < nwords) bits = s_alive[w];
-    m = bits ? ((w << 5) + __ffs(bits) - 1) : INT_MAX;
+    if (kept >= D) break;
+
+    // window exhausted: its suppressed candidates, in rank order, extend the output tail
+    if (ntail < D) {
+      bool dead = valid && !alive;
+      unsigned db = __ballot_sync(0xffffffffu, dead);
+      if (lane == 0) s_wsum[warp] = __popc(db);
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int q = 0; q < 32; q++) {
+        int v = s_wsum[q];
+        if (q < warp) woff += v;
+        tot += v;
+      }
+      int pos = ntail + woff + __popc(db & ((1u << lane) - 1u));
+      if (dead && pos < D) sm.d.tidx[pos] = idx;
+      ntail += tot;
+      __syncthreads();
+    }
   }
   __syncthreads();
 
-  // ---- 4. tail: first suppressed ranks, only when fewer than min(D, n) were kept ---------
-  if (kept < nd) {
-    // here the loop ran to exhaustion: every rank < n is either kept (alive) or suppressed
-    const int need = nd - kept;
-    int base = 0;
-    for (int k = 0; k < kMaxRanks && base < need; k++) {
-      int r = t + k * kThreads;
-      bool dead = (r < n) && !((alive >> k) & 1u);
-      unsigned bal = __ballot_sync(0xffffffffu, dead);
-      int wcount = __popc(bal);
-      __syncthreads();
-      if (lane == 0) s_wsum[warp] = wcount;
-      __syncthreads();
-      int woff = 0, tot = 0;
-      for (int w = 0; w < 32; w++) {
-        int v = s_wsum[w];
-        if (w < warp) woff += v;
-        tot += v;
-      }
-      int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
-      if (dead && pos < need) s_tail[pos] = r;
-      base += tot;
-    }
-    __syncthreads();
-  }
-
-  // ---- 5. outputs (nms.cu:150-156) --------------------------------------------------------
+  // ---- 3. outputs (nms.cu:150-156): kept..., then suppressed (score 0) up to min(D, n) ----
   float *os = p.out_scores + (long long)img * D;
   float *ob = p.out_boxes + (long long)img * D * NBOX;
   float *oc = p.out_classes + (long long)img * D;
   int32_t *oi = p.out_index ? p.out_index + (long long)img * D : nullptr;
   for (int j = t; j < D; j += kThreads) {
     if (j < nd) {
-      int r = (j < kept) ? s_kept[j] : s_tail[j - kept];
-      int i = sidx[r];
+      int i = (j < kept) ? sm.d.kidx[j] : sm.d.tidx[j - kept];
       os[j] = (j < kept) ? sc[i] : 0.0f;
 #pragma unroll
-      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = sbox[r * NBOX + q];
+      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = bx[(long long)i * NBOX + q];
       oc[j] = cl[i];
       if (oi) oi[j] = i;
     } else {
@@ -347,11 +360,11 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
 
 template <int NBOX>
 long long launch_nms(const NmsParams &p, int batch, cudaStream_t stream) {
-  size_t smem = NmsSmem<NBOX>::total(p.count);
+  const size_t smem = sizeof(typename NmsSmem<NBOX>::U);
   static bool configured = false;  // per template instance
   if (!configured) {
     if (cudaFuncSetAttribute(nms_batched_kernel<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)NmsSmem<NBOX>::total(kMaxCount)) != cudaSuccess)
+                             (int)smem) != cudaSuccess)
       return ODTK_E_CUDA;
     configured = true;
   }
