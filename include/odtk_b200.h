@@ -117,6 +117,37 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
                       int32_t *out_index, void *workspace, size_t workspace_size,
                       odtk_stream_t stream);
 
+/* ---- convolution engine ----------------------------------------------------------
+ * Replaces the nn.Conv2d (+ BatchNorm + ReLU + residual / FPN upsample-add) library
+ * calls of the reference's Model.forward (odtk/model.py:57-68,130-135;
+ * odtk/backbones/fpn.py:45-61; torchvision resnet blocks): the reference has no
+ * convolution kernel of its own (cuDNN through PyTorch).  Activations are NHWC fp16,
+ * weights [Cout, ksize*ksize*Cin] fp16 (tap-major, channel-minor), fp32 accumulation.
+ * odtk_conv2d handles stride-1 1x1 and 3x3 (pad 1) convolutions with Cin % 64 == 0 on
+ * the tensor cores; strided / 7x7 convolutions are first lowered to GEMM rows with
+ * odtk_lower_conv and then run as a 1x1 convolution over the lowered matrix.        */
+#define ODTK_OUT_NHWC_F16 0          /* y: [N, H, W, ldy] fp16                          */
+#define ODTK_OUT_NCHW_F32 1          /* y: [N, Cout, H, W] fp32 (box head output)       */
+#define ODTK_OUT_NCHW_F32_SIGMOID 2  /* same, sigmoid applied (odtk/model.py:140)       */
+typedef struct {
+  const void *x;        /* NHWC fp16 [n, h, width, cin]                                 */
+  const void *w;        /* fp16 [cout, ksize*ksize*cin]                                 */
+  const float *bias;    /* fp32 [cout] or NULL (conv bias or folded BatchNorm shift)    */
+  const void *residual; /* NHWC fp16 [n, h, width, ldr] added before ReLU, or NULL      */
+  const void *upsample; /* NHWC fp16 [n, h/2, width/2, cout] nearest-upsampled and added */
+  void *y;
+  int n, h, width, cin, cout, ksize, relu, out_mode, ldy, ldr;
+} odtk_conv_t;
+int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
+
+/* Gather the receptive fields of a ksize x ksize / stride / pad convolution over NHWC
+ * fp16 x into out[pixels, kpad] (tap-major, channel-minor, zero padded to kpad columns;
+ * relu != 0 applies ReLU to the gathered values: FPN pyramid7 input, fpn.py:55).     */
+int odtk_lower_conv(const void *x, void *out, int n, int h, int w, int c, int ksize, int stride, int pad,
+                    int kpad, int relu, odtk_stream_t stream);
+/* 3x3 stride-2 pad-1 max-pool, NHWC fp16 (torchvision resnet stem).                  */
+int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, int c, odtk_stream_t stream);
+
 /* ---- per-kernel timing (B200-native addition; the reference has only a wall-clock
  * Profiler without CUDA sync, odtk/utils.py:140-167) ------------------------------
  * When enabled, every launch of a tagged kernel is bracketed by CUDA events on the

@@ -1,0 +1,17 @@
+// conv.cuh -- kernel-side parameter block of conv_gemm_kernel (see conv.cu).
+#pragma once
+#include <cuda_fp16.h>
+
+struct ConvParams {
+  int mode;             // 0: rows of a [M, Cin] matrix (1x1 conv / lowered conv); 1: spatial patches (3x3, pad 1)
+  int N, H, W, Cin, Cout;
+  int taps, kw, pad;    // 1 / 9 taps
+  int TH, TW, tiles_h, tiles_w;   // mode 1: patch and patches per image
+  int num_m_tiles, num_n_tiles, BN, kblocks_per_tap;
+  long long M;          // N*H*W
+  const float *bias;    // [Cout] fp32 (folded BatchNorm shift / conv bias) or NULL
+  const __half *residual;  // NHWC fp16, row stride ldr, or NULL
+  const __half *upsample;  // NHWC fp16 [N, H/2, W/2, Cout] (FPN top-down path) or NULL
+  void *out;
+  int relu, out_mode, ldy, ldr, up_h, up_w;
+};

@@ -1,0 +1,140 @@
+// layers.cu -- the small memory-bound layers around the tensor-core convolution:
+//   * lowering of strided / 7x7 convolutions to GEMM rows (gather of the receptive field into
+//     a [pixels, taps*C] fp16 matrix; used for the ResNet stem, the three stride-2 3x3 and 1x1
+//     convolutions of the backbone, and FPN pyramid6 / pyramid7 -- together < 5 % of the FLOPs);
+//   * 3x3 stride-2 max-pool (torchvision resnet.py maxpool), NHWC fp16.
+// Reference call sites: odtk/backbones/resnet.py:25-28, odtk/backbones/fpn.py:54-55.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace {
+
+// C % 8 == 0: one thread moves 8 channels (16 B) of one tap of one output pixel.
+__global__ void lower_vec8_kernel(const __half *__restrict__ x, __half *__restrict__ out, int N, int H, int W, int C,
+                                  int OH, int OW, int ks, int stride, int pad, int kpad, int relu) {
+  const int c8n = C >> 3;
+  const long long total = (long long)N * OH * OW * ks * ks * c8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % c8n);
+    long long r = i / c8n;
+    int tap = (int)(r % (ks * ks));
+    long long m = r / (ks * ks);
+    int ow = (int)(m % OW);
+    long long t = m / OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    int ih = oh * stride + tap / ks - pad, iw = ow * stride + tap % ks - pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)n * H + ih) * W + iw) * C + c8 * 8));
+      if (relu) {
+        __half2 *h = reinterpret_cast<__half2 *>(&v);
+        const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int j = 0; j < 4; j++) h[j] = __hmax2(h[j], z);
+      }
+    }
+    *reinterpret_cast<uint4 *>(out + m * kpad + (long long)tap * C + c8 * 8) = v;
+  }
+}
+
+// generic small-C path (the RGB stem): one thread produces 8 consecutive K entries.
+__global__ void lower_generic_kernel(const __half *__restrict__ x, __half *__restrict__ out, int N, int H, int W, int C,
+                                     int OH, int OW, int ks, int stride, int pad, int kpad) {
+  const int k8n = kpad >> 3;
+  const int kreal = ks * ks * C;
+  const long long total = (long long)N * OH * OW * k8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k8 = (int)(i % k8n);
+    long long m = i / k8n;
+    int ow = (int)(m % OW);
+    long long t = m / OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int k = k8 * 8 + j;
+      __half val = __float2half_rn(0.0f);
+      if (k < kreal) {
+        int tap = k / C, c = k - tap * C;
+        int ih = oh * stride + tap / ks - pad, iw = ow * stride + tap % ks - pad;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = x[(((long long)n * H + ih) * W + iw) * C + c];
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<uint4 *>(out + m * kpad + k8 * 8) = *reinterpret_cast<uint4 *>(v);
+  }
+}
+
+__global__ void maxpool3x3s2_kernel(const __half *__restrict__ x, __half *__restrict__ y, int N, int H, int W, int C,
+                                    int OH, int OW) {
+  const int c8n = C >> 3;
+  const long long total = (long long)N * OH * OW * c8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % c8n);
+    long long m = i / c8n;
+    int ow = (int)(m % OW);
+    long long t = m / OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    __half2 best[4];
+    const __half2 ninf = __float2half2_rn(-65504.0f);
+#pragma unroll
+    for (int j = 0; j < 4; j++) best[j] = ninf;
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++) {
+      int ih = oh * 2 + dy - 1;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) {
+        int iw = ow * 2 + dx - 1;
+        if (iw < 0 || iw >= W) continue;
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)n * H + ih) * W + iw) * C + c8 * 8));
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) best[j] = __hmax2(best[j], h[j]);
+      }
+    }
+    *reinterpret_cast<uint4 *>(y + m * C + c8 * 8) = *reinterpret_cast<uint4 *>(best);
+  }
+}
+
+inline int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  long long cap = 148ll * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int odtk_lower_conv(const void *x, void *out, int n, int h, int w, int c, int ksize, int stride, int pad,
+                               int kpad, int relu, odtk_stream_t stream_) {
+  if (!x || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || ksize <= 0 || stride <= 0 || pad < 0) return ODTK_E_INVALID;
+  if (kpad < ksize * ksize * c || (kpad % 8)) return ODTK_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+  if (c % 8 == 0) {
+    if (kpad != ksize * ksize * c) return ODTK_E_INVALID;
+    long long total = (long long)n * oh * ow * ksize * ksize * (c / 8);
+    lower_vec8_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half *)x, (__half *)out, n, h, w, c, oh, ow,
+                                                                ksize, stride, pad, kpad, relu);
+  } else {
+    if (relu) return ODTK_E_UNSUPPORTED;
+    long long total = (long long)n * oh * ow * (kpad / 8);
+    lower_generic_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half *)x, (__half *)out, n, h, w, c, oh,
+                                                                   ow, ksize, stride, pad, kpad);
+  }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, int c, odtk_stream_t stream_) {
+  if (!x || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return ODTK_E_INVALID;
+  const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+  long long total = (long long)n * oh * ow * (c / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w,
+                                                                               c, oh, ow);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}

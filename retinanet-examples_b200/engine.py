@@ -1,0 +1,79 @@
+"""Thin host wrappers over the convolution engine of the C ABI (include/odtk_b200.h): weight
+packing / BatchNorm folding and per-layer calls.  Activations are NHWC fp16 CUDA tensors."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+OUT_NHWC_F16, OUT_NCHW_F32, OUT_NCHW_F32_SIGMOID = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    """odtk_conv_t (include/odtk_b200.h)."""
+    _fields_ = [("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("residual", ctypes.c_void_p), ("upsample", ctypes.c_void_p), ("y", ctypes.c_void_p),
+                ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
+                ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
+                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int)]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def fold_bn(weight, bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
+    """conv (no bias) followed by eval-mode BatchNorm == conv with scaled weights + a bias
+    (torchvision BasicBlock/Bottleneck, odtk/backbones/layers.py:5-15).  fp32 in, fp32 out."""
+    scale = bn_weight.float() / torch.sqrt(running_var.float() + eps)
+    return weight.float() * scale.view(-1, 1, 1, 1), bn_bias.float() - running_mean.float() * scale
+
+
+def pack_weight(weight, kpad=None):
+    """[Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw*Cin (zero padded to kpad)] fp16, tap-major /
+    channel-minor: the K order of the kernel's (tap, 64-channel chunk) loop."""
+    cout, cin, kh, kw = weight.shape
+    w = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    if kpad is not None and kpad > w.shape[1]:
+        w = torch.cat([w, w.new_zeros(cout, kpad - w.shape[1])], dim=1)
+    return w.to(torch.float16).contiguous()
+
+
+def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None):
+    """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
+    Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
+    n, h, wd, cin = x.shape
+    if out is None:
+        if out_mode == OUT_NHWC_F16:
+            out = torch.empty((n, h, wd, cout), dtype=torch.float16, device=x.device)
+        else:
+            out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+    d = ConvDesc()
+    d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.upsample = upsample.data_ptr() if upsample is not None else None
+    d.n, d.h, d.width, d.cin, d.cout, d.ksize = n, h, wd, cin, cout, ksize
+    d.relu, d.out_mode, d.ldy, d.ldr = int(relu), out_mode, 0, 0
+    _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
+    return out
+
+
+def lower_conv(x, ksize, stride, pad, kpad=None, relu=False):
+    """Gather receptive fields: NHWC fp16 [N,H,W,C] -> [N, OH, OW, kpad] fp16."""
+    n, h, w, c = x.shape
+    oh, ow = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+    kpad = kpad or ksize * ksize * c
+    out = torch.empty((n, oh, ow, kpad), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().odtk_lower_conv(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
+                                          ksize, stride, pad, kpad, int(relu), _stream()), "lower_conv")
+    return out
+
+
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().odtk_maxpool3x3s2(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
+                                            _stream()), "maxpool3x3s2")
+    return out

@@ -1,0 +1,110 @@
+"""GPU parity tests of the tensor-core convolution engine (conv.cu / layers.cu) through the C ABI,
+against torch's fp32 CPU convolution of the same fp16-rounded operands (the arithmetic the
+reference's nn.Conv2d performs; torch is the oracle for this floating-point kernel).
+
+Tolerance: operands are identical fp16 values on both sides, products are exact in fp32, so the only
+differences are fp32 accumulation order and the final fp16 rounding of the output:
+|err| <= 2e-3 * max|y| + 1e-3 for fp16 outputs, 1e-4 relative for fp32 outputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from retinanet_examples_b200 import engine
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).to(torch.float16)
+
+
+def _ref_conv(x_nhwc, w, bias, ksize, relu=False, residual=None, upsample=None, stride=1, pad=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w.float(), bias.float() if bias is not None else None, stride=stride,
+                 padding=ksize // 2 if pad is None else pad)
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if upsample is not None:
+        y = y + F.interpolate(upsample.float().permute(0, 3, 1, 2), scale_factor=2)
+    if relu:
+        y = F.relu(y)
+    return y   # NCHW fp32
+
+
+def _close16(got_nhwc, ref_nchw):
+    ref = ref_nchw.permute(0, 2, 3, 1)
+    err = (got_nhwc.float().cpu() - ref).abs().max().item()
+    tol = 2e-3 * ref.abs().max().item() + 1e-3
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 16, 64, 64), (2, 13, 20, 256, 256), (1, 25, 40, 128, 512),
+                                           (3, 7, 10, 512, 128), (1, 50, 80, 1024, 256), (2, 5, 5, 2048, 512)])
+def test_conv1x1_matches_torch(n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(n * 1000 + cin + cout)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 1, 1), g, 0.05), torch.randn(cout, generator=g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 1, relu=True)
+    _close16(y, _ref_conv(x, wt, b, 1, relu=True))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 16, 64, 64), (2, 13, 20, 256, 256), (1, 25, 40, 128, 128),
+                                           (2, 7, 10, 256, 256), (1, 100, 160, 64, 64), (1, 50, 80, 512, 512),
+                                           (2, 3, 3, 256, 256), (1, 33, 47, 128, 256)])
+def test_conv3x3_matches_torch(n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(h * 100 + w + cin)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 3, 3), g, 0.03), torch.randn(cout, generator=g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 3)
+    _close16(y, _ref_conv(x, wt, b, 3))
+
+
+def test_conv_epilogue_residual_relu_and_upsample_add():
+    g = torch.Generator().manual_seed(5)
+    n, h, w, cin, cout = 2, 26, 40, 256, 256
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 1, 1), g, 0.05), torch.randn(cout, generator=g)
+    res, up = _rand((n, h, w, cout), g), _rand((n, h // 2, w // 2, cout), g)
+    pw = engine.pack_weight(wt.float()).to(DEV)
+    y = engine.conv2d(x.to(DEV), pw, b.to(DEV), cout, 1, relu=True, residual=res.to(DEV))
+    _close16(y, _ref_conv(x, wt, b, 1, relu=True, residual=res))
+    y = engine.conv2d(x.to(DEV), pw, b.to(DEV), cout, 1, upsample=up.to(DEV))
+    _close16(y, _ref_conv(x, wt, b, 1, upsample=up))
+    y = engine.conv2d(x.to(DEV), pw, None, cout, 1)
+    _close16(y, _ref_conv(x, wt, None, 1))
+
+
+@pytest.mark.parametrize("cout,mode", [(720, engine.OUT_NCHW_F32_SIGMOID), (36, engine.OUT_NCHW_F32),
+                                       (162, engine.OUT_NCHW_F32), (720, engine.OUT_NCHW_F32)])
+def test_head_final_conv_nchw_fp32(cout, mode):
+    g = torch.Generator().manual_seed(cout)
+    n, h, w, cin = 2, 25, 40, 256
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 3, 3), g, 0.02), torch.randn(cout, generator=g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 3, out_mode=mode)
+    ref = _ref_conv(x, wt, b, 3)
+    if mode == engine.OUT_NCHW_F32_SIGMOID:
+        ref = torch.sigmoid(ref)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("c,ks,stride,pad", [(64, 3, 2, 1), (128, 1, 2, 0), (256, 3, 2, 1), (3, 7, 2, 3)])
+def test_lowered_strided_conv(c, ks, stride, pad):
+    """stride-2 / 7x7 convolutions = receptive-field gather + GEMM rows."""
+    g = torch.Generator().manual_seed(c * 10 + ks)
+    n, h, w, cout = 2, 26, 38, 64
+    x, wt, b = _rand((n, h, w, c), g), _rand((cout, c, ks, ks), g, 0.05), torch.randn(cout, generator=g)
+    kreal = ks * ks * c
+    kpad = (kreal + 63) // 64 * 64
+    low = engine.lower_conv(x.to(DEV), ks, stride, pad, kpad=kpad if c % 8 else None)
+    if c % 8 == 0:
+        assert kreal % 64 == 0
+    y = engine.conv2d(low, engine.pack_weight(wt.float(), kpad).to(DEV), b.to(DEV), cout, 1, relu=True)
+    _close16(y, _ref_conv(x, wt, b, ks, relu=True, stride=stride, pad=pad))
+
+
+def test_maxpool_matches_torch():
+    g = torch.Generator().manual_seed(9)
+    x = _rand((2, 21, 30, 64), g)
+    y = engine.maxpool3x3s2(x.to(DEV))
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    np.testing.assert_array_equal(y.float().cpu().numpy(), ref.numpy())
