@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- the driver-facing benchmark of the RetinaNet inference hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload full|postproc]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-One JSON line on rank 0.  A "step" is one pass of the hot path over one batch of synthetic
-input.  `value` is device-timed whole-job throughput with inputs resident in HBM; `e2e` is the
-same metric through the public API with HOST (pinned) buffers and the host<->device copies
-inside the timed region; `roofline` describes the dominant kernel (live CUDA-event timing on the
-launching stream); `cpu_baseline` is the CPU oracle timed on this box's host cores (rank 0, N=1).
+One JSON line on rank 0.  A "step" is one pass of the hot path over one batch of synthetic input:
+`full` (default, BASELINE.json configs[2]) = Model.forward: backbone + FPN + heads + decode + NMS
+on [B, 3, 800, 1280] fp16; `postproc` (configs[1]) = decode + NMS on pre-computed head outputs.
+`value` is device-timed whole-job throughput with inputs resident in HBM; `e2e` is the same metric
+through the public API with HOST (pinned) buffers and the host<->device copies inside the timed
+region; `roofline` describes the dominant kernel (live CUDA-event timing on the launching stream);
+`cpu_baseline` is the CPU oracle timed on this box's host cores (rank 0, N=1).  With N > 1 every rank
+runs the same per-GPU batch on its own images (weak scaling, image-wise sharding) and the detections
+of all ranks are gathered with one NCCL all-gather per step inside the timed region.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -59,7 +64,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         for (t, line) in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -68,6 +73,7 @@ class ClockSampler:
                 mx = float(f[1])
                 if t0 - 0.05 <= t <= t1 + 0.05:
                     sm.append(float(f[0]))
+                    power.append(float(f[2]))
                     for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                         if v.lower().startswith("active"):
                             reasons.add(name)
@@ -81,14 +87,122 @@ class ClockSampler:
                     pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def _prof_get(lib, tag):
+    ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+    lib.odtk_prof_get(tag, ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, n.value
+
+
+# =================================================================================================
+# workload: full model (BASELINE.json configs[2]: ResNet50FPN fp16, batch 32 per GPU, 3x800x1280)
+# =================================================================================================
+class FullWorkload:
+    metric = "images/sec (3x800x1280 fp16, backbone+FPN+heads+decode+NMS)"
+    dtype = "f16"
+    H, W = 800, 1280
+
+    def __init__(self, backbone, batch, rank, device):
+        import torch
+        from retinanet_examples_b200 import engine, synth
+        from retinanet_examples_b200.model import Model, make_state_dict
+        self.torch, self.batch, self.device, self.engine = torch, batch, device, engine
+        self.backbone = backbone
+        self.name = "%s fp16, batch %d per GPU, full backbone+FPN+heads+decode+NMS, 3x800x1280 (BASELINE configs[2])" % (backbone, batch)
+        g = torch.Generator().manual_seed(1000 + rank)
+        self.host_x = torch.randn((batch, 3, self.H, self.W), generator=g).to(torch.float16) \
+            .contiguous(memory_format=torch.channels_last).pin_memory()
+        self.dev_x = self.host_x.to(device)
+        sd = make_state_dict(backbone, 80, 9, False, seed=0)
+        model = Model(backbone, classes=80)
+
+        def gpu_logits(s):   # probe: 2 images through the CUDA engine
+            model.load_state_dict(s).cuda(device.index)
+            return model.forward_heads(self.dev_x[:2], sigmoid=False)[0]
+        self.sd = synth.calibrate_cls_head(sd, gpu_logits)
+        self.model = model.load_state_dict(self.sd).cuda(device.index)
+        self.det = self.model.detections
+        self.h2d_bytes = self.host_x.numel() * 2
+        self.d2h_bytes = batch * self.det * 6 * 4
+        self.host_out = torch.empty((batch, self.det, 6), dtype=torch.float32).pin_memory()
+        self.out = None
+        engine.STATS["launches"] = engine.STATS["conv_flops"] = 0
+        self.step()
+        torch.cuda.synchronize()
+        self.launches_per_step = engine.STATS["launches"] + 4       # + decode (3) + nms (1)
+        self.flops_per_step = engine.STATS["conv_flops"]
+        self.world_gather = None
+
+    def _gather(self, out):
+        if self.world_gather:
+            from retinanet_examples_b200 import infer
+            return infer.gather_detections(*out, world=self.world_gather)
+        return out
+
+    def step(self):
+        self.out = self._gather(self.model(self.dev_x))
+
+    def step_e2e(self):
+        from retinanet_examples_b200 import infer
+        x = self.host_x.to(self.device, non_blocking=True)
+        s, b, c = self.model(x)
+        self.host_out.copy_(infer.pack_detections(s, b, c), non_blocking=True)
+        self._gather((s, b, c))
+        self.torch.cuda.current_stream().synchronize()
+
+    def units_per_step(self):
+        return self.batch
+
+    def config(self):
+        n_det = int((self.out[0] > 0).sum().item())
+        return {"workload": self.name, "images_per_gpu": self.batch, "classes": 80, "anchors": 9,
+                "conv_gflop_per_image": round(self.flops_per_step / self.batch / 1e9, 2),
+                "weights": "random init (seed 0), BatchNorm folded, class head calibrated to ~0.56% scores > 0.05",
+                "detections_in_last_step": n_det,
+                "l2": "activations of a step (GBs) exceed the 126 MB L2; input batch %.0f MB" % (self.h2d_bytes / 1e6)}
+
+    def roofline(self, lib, peaks, steps):
+        ms, n = _prof_get(lib, 3)
+        if n == 0:
+            return None
+        flops = float(self.flops_per_step) * steps
+        achieved = flops / (ms * 1e-3) / 1e12
+        peak = peaks["tensor_sustained"] or peaks["tensor"]
+        return {"kernel": "conv_gemm_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "traffic": None,
+                "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
+                "avg_launch_ms": round(ms / n, 5), "launches_timed": n,
+                "algorithmic_flops_per_step": int(self.flops_per_step),
+                "conv_share_of_step": None}
+
+    # ---- CPU legs (oracle port of the reference's PyTorch-CPU path; rank 0 only) --------------------
+    @staticmethod
+    def cpu_run(backbone, sd, nimg, reps, H=800, W=1280):
+        import torch
+        from oracle import model_ref
+        torch.set_num_threads(os.cpu_count() or 1)
+        x = torch.randn((nimg, 3, H, W), generator=torch.Generator().manual_seed(7))
+        model_ref.forward(sd, backbone, x[:1])        # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            model_ref.forward(sd, backbone, x)
+        dt = time.perf_counter() - t0
+        return nimg * reps / dt, torch.get_num_threads()
+
+    def cpu_baseline(self):
+        v, cores = self.cpu_run(self.backbone, self.sd, 1, 2)
+        return {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
+                "sample": "2 x 1 image 3x800x1280 fp32, oracle/model_ref.py (torch CPU convs, same weights) + "
+                          "oracle decode/nms; the reference's own PyTorch-CPU path restated"}
 
 
 # =================================================================================================
 # workload: decode + NMS only (BASELINE.json configs[1]: RN50FPN head shapes, batch 8 per GPU)
 # =================================================================================================
 class PostprocWorkload:
-    name = "decode+nms only, ResNet50FPN head shapes 3x800x1280, 80 classes, 9 anchors (BASELINE configs[1])"
     metric = "decode+NMS images/sec (3x800x1280 head outputs, fp32 NCHW entry point)"
     dtype = "f32"
 
@@ -96,7 +210,7 @@ class PostprocWorkload:
         import torch
         from retinanet_examples_b200 import box, synth
         self.torch, self.batch, self.device = torch, batch, device
-        self.box = box
+        self.name = "decode+nms only, ResNet50FPN head shapes 3x800x1280, 80 classes, 9 anchors, batch %d (BASELINE configs[1])" % batch
         cls, deltas = synth.head_outputs(batch, seed=rank)
         self.host = [(c.pin_memory(), d.pin_memory()) for c, d in zip(cls, deltas)]
         self.dev = [(c.to(device), d.to(device)) for c, d in self.host]
@@ -109,13 +223,11 @@ class PostprocWorkload:
         self.out = None
         self.host_out = torch.empty((batch, self.det, 6), dtype=torch.float32).pin_memory()
         self.launches_per_step = 3 + 1   # filter, gather, select+decode (all levels), nms
-        # algorithmic bytes of the dominant kernel (score filter at P3): scores read once
-        self.dominant = {"tag": 0, "name": "score_filter_kernel", "bound": "hbm"}
         self.level_score_bytes = [c.numel() * 4 for c, _ in self.host]
+        self.world_gather = None
 
     def _run(self, tensors):
         from retinanet_examples_b200 import _C
-        torch = self.torch
         scores, boxes, classes = _C.decode_levels([c for c, _ in tensors], [d for _, d in tensors], self.anchors,
                                                   self.strides, 0.05, self.top_n, False)
         return _C.nms(scores, boxes, classes, 0.5, self.det, False)
@@ -134,24 +246,25 @@ class PostprocWorkload:
     def units_per_step(self):
         return self.batch
 
-    def roofline(self, lib, peaks):
-        import ctypes
-        ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
-        lib.odtk_prof_get(self.dominant["tag"], ctypes.byref(ms), ctypes.byref(n))
-        if n.value == 0:
+    def config(self):
+        return {"workload": self.name, "images_per_gpu": self.batch, "top_n": 1000, "detections": 100,
+                "threshold": 0.05, "nms": 0.5,
+                "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2" % (self.h2d_bytes / 1e6)}
+
+    def roofline(self, lib, peaks, steps):
+        ms, n = _prof_get(lib, 0)
+        if n == 0:
             return None
-        # one launch per step covers all five levels; algorithmic bytes = every score read once
         bytes_per_launch = float(sum(self.level_score_bytes))
-        avg_ms = ms.value / n.value
+        avg_ms = ms / n
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        return {"kernel": self.dominant["name"], "bound": "hbm", "achieved": round(achieved, 1),
+        return {"kernel": "score_filter_kernel", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peaks["hbm"], "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
                 "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                "avg_launch_ms": round(avg_ms, 5), "launches_timed": n.value,
+                "avg_launch_ms": round(avg_ms, 5), "launches_timed": n,
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "note": "one launch per step streams the scores of all 5 levels of the batch"}
 
-    # ---- CPU legs (oracle; rank 0 only) --------------------------------------------------------
     def cpu_once(self, nimg):
         import numpy as np
         from oracle import oracle
@@ -175,14 +288,18 @@ class PostprocWorkload:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="postproc", choices=["postproc"])
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU")
+    ap.add_argument("--workload", default="full", choices=["full", "postproc"])
+    ap.add_argument("--backbone", default="ResNet50FPN")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 32 full, 8 postproc)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if not args.batch:
+        args.batch = 32 if args.workload == "full" else 8
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -204,7 +321,10 @@ def main():
     lib = _lib.lib()
     peaks = _peaks()
 
-    wl = PostprocWorkload(args.batch, rank, device)
+    wl = FullWorkload(args.backbone, args.batch, rank, device) if args.workload == "full" else \
+        PostprocWorkload(args.batch, rank, device)
+    if world > 1:
+        wl.world_gather = world
 
     def barrier():
         if world > 1:
@@ -229,40 +349,51 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
-    for _ in range(args.warmup):
-        wl.step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    ms, t0, t1 = timed(wl.step, args.steps, profile=True)
-    roof = wl.roofline(lib, peaks)
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-
-    for _ in range(2):
-        wl.step_e2e()
-    ms_e2e, _, _ = timed(wl.step_e2e, args.steps, profile=False)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            wl.step()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        # pass 1: the measured value (no per-kernel events in the stream)
+        ms, t0, t1 = timed(wl.step, args.steps, profile=False)
+        clocks = sampler.stop(t0, t1) if rank == 0 else None
+        # pass 2: same steps with the dominant kernel bracketed by CUDA events (roofline numbers)
+        ms_prof, _, _ = timed(wl.step, args.steps, profile=True)
+        roof = wl.roofline(lib, peaks, args.steps)
+        if roof is not None and "conv_share_of_step" in roof:
+            cms, _ = _prof_get(lib, 3)
+            roof["conv_share_of_step"] = round(cms / ms_prof, 4)
+        ms_e2e = None
+        if not args.no_e2e:
+            for _ in range(2):
+                wl.step_e2e()
+            ms_e2e, _, _ = timed(wl.step_e2e, args.steps, profile=False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     units = wl.units_per_step() * world
+    cfg = wl.config()
+    cfg.update({"global_batch": units,
+                "parallelism": ("image-wise sharding over %d GPUs, one NCCL all-gather of the packed detections per step" % world)
+                if world > 1 else "single GPU"})
     out = {
         "metric": wl.metric, "value": round(units * args.steps / (ms * 1e-3), 2), "unit": "images/sec",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "images_per_gpu": args.batch, "global_batch": units, "top_n": 1000,
-                   "detections": 100, "threshold": 0.05, "nms": 0.5, "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2"
-                   % (wl.h2d_bytes / 1e6), "sharding": "image-wise, no data-path collective" if world > 1 else "single GPU"},
+        "config": cfg,
         "us_per_image": round(ms * 1e3 / args.steps / wl.units_per_step(), 3),
         "clocks": clocks,
-        "e2e": {"value": round(units * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/sec",
-                "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
-                "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": wl.launches_per_step * args.steps,
         "roofline": roof,
     }
+    if ms_e2e is not None:
+        out["e2e"] = {"value": round(units * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/sec",
+                      "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
+                      "ms_per_step": round(ms_e2e / args.steps, 4)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = wl.cpu_baseline()
     print(json.dumps(out), flush=True)
@@ -271,34 +402,51 @@ def main():
 
 
 def reference_arm(args, rank, world):
-    """The reference's CPU implementation of the path on this box's host cores (the oracle port:
-    /root/reference does not exist on the GPU box).  Rank 0 only; other ranks exit 0."""
+    """The reference's CPU implementation of the path on this box's host cores.  /root/reference
+    (Python) cannot travel to the GPU box, so this is the oracle port: oracle/model_ref.py (the same
+    torch CPU convolutions nn.Conv2d runs) + oracle decode/nms, all host threads torch can use.
+    Rank 0 only; other ranks exit 0."""
     if rank != 0:
         return
     import torch
-    wl = PostprocWorkload.__new__(PostprocWorkload)
-    from retinanet_examples_b200 import box, synth
-    nimg = 2
-    cls, deltas = synth.head_outputs(nimg, seed=0)
-    wl.torch, wl.batch, wl.box = torch, nimg, box
-    wl.host = list(zip(cls, deltas))
-    wl.anchors = [box.generate_anchors(s, box.DEFAULT_RATIOS, box.DEFAULT_SCALES).reshape(-1).tolist() for s in synth.LEVEL_STRIDES]
-    wl.strides, wl.top_n, wl.det = synth.LEVEL_STRIDES, 1000, 100
-    for _ in range(min(args.warmup, 1)):
-        wl.cpu_once(nimg)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        wl.cpu_once(nimg)
-    dt = time.perf_counter() - t0
-    v = round(nimg * steps / dt, 3)
-    sample = "%d steps x %d images, all 5 levels, oracle decode+nms (port of csrc/cuda semantics), 1 thread" % (steps, nimg)
+    if args.workload == "postproc":
+        from retinanet_examples_b200 import box, synth
+        wl = PostprocWorkload.__new__(PostprocWorkload)
+        nimg = 2
+        cls, deltas = synth.head_outputs(nimg, seed=0)
+        wl.torch, wl.batch = torch, nimg
+        wl.host = list(zip(cls, deltas))
+        wl.anchors = [box.generate_anchors(s, box.DEFAULT_RATIOS, box.DEFAULT_SCALES).reshape(-1).tolist() for s in synth.LEVEL_STRIDES]
+        wl.strides, wl.top_n, wl.det = synth.LEVEL_STRIDES, 1000, 100
+        wl.cpu_once(1)
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            wl.cpu_once(nimg)
+        dt = time.perf_counter() - t0
+        v, cores, metric, dtype = nimg * steps / dt, 1, PostprocWorkload.metric, "f32"
+        name = "decode+nms only, ResNet50FPN head shapes 3x800x1280 (BASELINE configs[1])"
+        sample = "%d steps x %d images, all 5 levels, oracle decode+nms, 1 thread" % (steps, nimg)
+    else:
+        from oracle import model_ref
+        from retinanet_examples_b200 import synth
+        from retinanet_examples_b200.model import make_state_dict
+        sd = make_state_dict(args.backbone, 80, 9, False, seed=0)
+        probe = torch.randn((1, 3, 256, 384), generator=torch.Generator().manual_seed(3))
+        sd = synth.calibrate_cls_head(sd, lambda s: model_ref.forward_heads(s, args.backbone, probe, sigmoid=False)[0])
+        steps = max(1, min(args.steps, 3))
+        v, cores = FullWorkload.cpu_run(args.backbone, sd, 1, steps)
+        dt = steps / v
+        metric, dtype = FullWorkload.metric, "f32"
+        name = "%s, full backbone+FPN+heads+decode+NMS, 3x800x1280 (BASELINE configs[2] workload on the CPU path)" % args.backbone
+        sample = "%d steps x 1 image 3x800x1280 fp32, oracle/model_ref.py torch-CPU convs + oracle decode/nms, %d threads" % (steps, cores)
+    v = round(v, 3)
     print(json.dumps({
-        "impl": "reference", "metric": PostprocWorkload.metric, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": PostprocWorkload.name, "images_per_step": nimg},
-        "cpu_baseline": {"value": v, "unit": "images/sec", "cores": 1, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": name, "images_per_step": 1 if args.workload == "full" else 2},
+        "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 

@@ -8,6 +8,10 @@ from . import _lib
 
 OUT_NHWC_F16, OUT_NCHW_F32, OUT_NCHW_F32_SIGMOID = 0, 1, 2
 
+# host-side accounting of what was launched (bench.py reads it): kernels launched by this
+# module and algorithmic convolution FLOPs (2 * pixels * Cout * taps * Cin, unpadded)
+STATS = {"launches": 0, "conv_flops": 0}
+
 
 class ConvDesc(ctypes.Structure):
     """odtk_conv_t (include/odtk_b200.h)."""
@@ -57,6 +61,7 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     d.n, d.h, d.width, d.cin, d.cout, d.ksize = n, h, wd, cin, cout, ksize
     d.relu, d.out_mode, d.ldy, d.ldr = int(relu), out_mode, 0, 0
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
+    STATS["launches"] += 1
     return out
 
 
@@ -68,6 +73,7 @@ def lower_conv(x, ksize, stride, pad, kpad=None, relu=False):
     out = torch.empty((n, oh, ow, kpad), dtype=torch.float16, device=x.device)
     _lib.check(_lib.lib().odtk_lower_conv(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
                                           ksize, stride, pad, kpad, int(relu), _stream()), "lower_conv")
+    STATS["launches"] += 1
     return out
 
 
@@ -76,4 +82,5 @@ def maxpool3x3s2(x):
     out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.float16, device=x.device)
     _lib.check(_lib.lib().odtk_maxpool3x3s2(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
                                             _stream()), "maxpool3x3s2")
+    STATS["launches"] += 1
     return out

@@ -1,0 +1,290 @@
+"""RetinaNet inference model -- host-side mirror of the reference's odtk/model.py `Model`
+(constructor arguments, `config` keys, state_dict key names, `forward(x) -> (scores, boxes,
+classes)`), executing on the sm_100a kernels behind the C ABI instead of nn.Conv2d/cuDNN +
+odtk._C.  Training (`_compute_loss`), checkpoint files and ONNX/TensorRT export are outside the
+hot path; `load_state_dict` ingests exactly the reference's key layout
+(odtk/model.py:217-258): `backbones.<Name>.features.*`, `backbones.<Name>.{lateral,pyramid,smooth}*`,
+`cls_head.{0,2,4,6,8}.*`, `box_head.{0,2,4,6,8}.*`.
+
+Data flow of forward() (reference: odtk/model.py:125-165, odtk/backbones/fpn.py:45-61,
+odtk/backbones/resnet.py:24-39, torchvision BasicBlock/Bottleneck):
+  NHWC fp16 activations; every conv is one launch of the tcgen05 kernel with BatchNorm folded
+  into weights/bias, ReLU / residual add / FPN upsample-add fused in its epilogue; the last conv
+  of each head writes fp32 NCHW (sigmoid fused for the class head) which feeds the all-levels
+  decode (3 launches) and the batched NMS (1 launch)."""
+import math
+
+import numpy as np
+import torch
+
+from . import _C, box, engine
+
+RESNET_LAYERS = {"ResNet18FPN": ("basic", [2, 2, 2, 2]), "ResNet34FPN": ("basic", [3, 4, 6, 3]),
+                 "ResNet50FPN": ("bottleneck", [3, 4, 6, 3]), "ResNet101FPN": ("bottleneck", [3, 4, 23, 3]),
+                 "ResNet152FPN": ("bottleneck", [3, 8, 36, 3])}
+
+
+def conv_specs(backbone, classes=80, num_anchors=9, rotated=False):
+    """Every convolution / batch-norm of the model as (state_dict prefix, kind, shape info), in
+    forward order.  kind: 'conv' (weight only, followed by 'bn') or 'convb' (weight + bias)."""
+    block, layers = RESNET_LAYERS[backbone]
+    f = "backbones.%s.features." % backbone
+    specs = [(f + "conv1", "conv", (64, 3, 7, 7)), (f + "bn1", "bn", 64)]
+    inplanes = 64
+    exp = 4 if block == "bottleneck" else 1
+    for li, (planes, nblocks) in enumerate(zip([64, 128, 256, 512], layers)):
+        for b in range(nblocks):
+            stride = 2 if (b == 0 and li > 0) else 1
+            p = f + "layer%d.%d." % (li + 1, b)
+            if block == "bottleneck":
+                specs += [(p + "conv1", "conv", (planes, inplanes, 1, 1)), (p + "bn1", "bn", planes),
+                          (p + "conv2", "conv", (planes, planes, 3, 3)), (p + "bn2", "bn", planes),
+                          (p + "conv3", "conv", (planes * 4, planes, 1, 1)), (p + "bn3", "bn_last", planes * 4)]
+            else:
+                specs += [(p + "conv1", "conv", (planes, inplanes, 3, 3)), (p + "bn1", "bn", planes),
+                          (p + "conv2", "conv", (planes, planes, 3, 3)), (p + "bn2", "bn_last", planes)]
+            if b == 0 and (stride != 1 or inplanes != planes * exp):
+                specs += [(p + "downsample.0", "conv", (planes * exp, inplanes, 1, 1)),
+                          (p + "downsample.1", "bn", planes * exp)]
+            inplanes = planes * exp
+    ch = [128, 256, 512] if block == "basic" else [512, 1024, 2048]
+    n = "backbones.%s." % backbone
+    specs += [(n + "lateral3", "convb", (256, ch[0], 1, 1)), (n + "lateral4", "convb", (256, ch[1], 1, 1)),
+              (n + "lateral5", "convb", (256, ch[2], 1, 1)), (n + "pyramid6", "convb", (256, ch[2], 3, 3)),
+              (n + "pyramid7", "convb", (256, 256, 3, 3)), (n + "smooth3", "convb", (256, 256, 3, 3)),
+              (n + "smooth4", "convb", (256, 256, 3, 3)), (n + "smooth5", "convb", (256, 256, 3, 3))]
+    nbox = 6 if rotated else 4
+    for head, out in (("cls_head", classes * num_anchors), ("box_head", nbox * num_anchors)):
+        for i in (0, 2, 4, 6):
+            specs.append(("%s.%d" % (head, i), "convb", (256, 256, 3, 3)))
+        specs.append(("%s.8" % head, "convb_final", (out, 256, 3, 3)))
+    return specs
+
+
+def make_state_dict(backbone="ResNet50FPN", classes=80, num_anchors=9, rotated=False, seed=0, cls_prior=0.01):
+    """Deterministic random-init weights in the reference's state_dict layout (no checkpoint or
+    pretrained weights exist offline).  BatchNorm statistics are randomised so that folding is
+    exercised; the last BN of each residual block is damped so
+    that activations stay well inside fp16 range through 50+ layers."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, kind, shp in conv_specs(backbone, classes, num_anchors, rotated):
+        if kind.startswith("conv"):
+            cout, cin, kh, kw = shp
+            std = 0.01 if name.startswith(("cls_head", "box_head")) else math.sqrt(2.0 / (cin * kh * kw))
+            sd[name + ".weight"] = torch.randn(shp, generator=g) * std
+            if kind != "conv":
+                sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.01
+                if kind == "convb_final" and name.startswith("cls_head"):
+                    sd[name + ".bias"] = torch.full((cout,), -math.log((1 - cls_prior) / cls_prior))
+        else:
+            c = shp
+            lo, hi = (0.1, 0.3) if kind == "bn_last" else (0.5, 1.5)
+            sd[name + ".weight"] = torch.rand(c, generator=g) * (hi - lo) + lo
+            sd[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+            sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+            sd[name + ".running_var"] = torch.rand(c, generator=g) + 0.5
+    return sd
+
+
+class _Conv:
+    """One packed convolution: fp16 weights in the kernel's K order, fp32 bias, geometry."""
+
+    def __init__(self, weight, bias, stride=1, device="cuda"):
+        cout, cin, kh, kw = weight.shape
+        self.cout, self.cin, self.ks, self.stride = cout, cin, kh, stride
+        self.direct = stride == 1 and kh in (1, 3) and cin % 64 == 0
+        kreal = kh * kw * cin
+        self.kpad = kreal if self.direct else (kreal + 63) // 64 * 64
+        self.w = engine.pack_weight(weight, self.kpad).to(device)
+        self.b = bias.float().contiguous().to(device) if bias is not None else None
+
+    def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False):
+        oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
+        engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin
+        if self.direct:
+            assert not in_relu
+            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode)
+        low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
+        return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode)
+
+
+class Model:
+    'RetinaNet - https://arxiv.org/abs/1708.02002 (reference: odtk/model.py:15-72)'
+
+    def __init__(self, backbones='ResNet50FPN', classes=80, ratios=[1.0, 2.0, 0.5],
+                 scales=[4 * 2 ** (i / 3) for i in range(3)], angles=None, rotated_bbox=False,
+                 anchor_ious=[0.4, 0.5], config={}):
+        if isinstance(backbones, (list, tuple)):
+            if len(backbones) != 1:
+                raise ValueError("one backbone per model on the B200 path")
+            backbones = backbones[0]
+        if backbones not in RESNET_LAYERS:
+            raise ValueError("unsupported backbone %r (hot path: %s)" % (backbones, ", ".join(RESNET_LAYERS)))
+        self.backbone = backbones
+        self.name = 'RetinaNet'
+        self.exporting = False
+        self.rotated_bbox = rotated_bbox
+        self.anchor_ious = anchor_ious
+        self.ratios, self.scales = ratios, scales
+        self.angles = angles if angles is not None else [-np.pi / 6, 0, np.pi / 6] if rotated_bbox else None
+        self.anchors = {}
+        self.classes = classes
+        self.threshold = config.get('threshold', 0.05)
+        self.top_n = config.get('top_n', 1000)
+        self.nms = config.get('nms', 0.5)
+        self.detections = config.get('detections', 100)
+        self.stride = 128
+        self.num_anchors = len(ratios) * len(scales) * (len(self.angles) if rotated_bbox else 1)
+        self._sd = None
+        self._packed = None
+        self.device = None
+
+    def __repr__(self):
+        return '\n'.join(['     model: {}'.format(self.name), '  backbone: {}'.format(self.backbone),
+                          '   classes: {}, anchors: {}'.format(self.classes, self.num_anchors)])
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def initialize(self, pre_trained=None, seed=0):
+        """Random init (reference: odtk/model.py:79-123; pre-trained checkpoints are unavailable)."""
+        if pre_trained:
+            raise ValueError("checkpoint files are outside the hot path; use load_state_dict()")
+        self.load_state_dict(make_state_dict(self.backbone, self.classes, self.num_anchors, self.rotated_bbox, seed))
+        return self
+
+    def state_dict(self):
+        return self._sd
+
+    def load_state_dict(self, sd):
+        need = [n + ".weight" for n, _, _ in conv_specs(self.backbone, self.classes, self.num_anchors, self.rotated_bbox)]
+        missing = [k for k in need if k not in sd]
+        if missing:
+            raise RuntimeError("missing keys in state_dict: %s" % missing[:4])
+        self._sd = {k: v.detach().float().cpu() for k, v in sd.items() if torch.is_tensor(v)}
+        self._packed = None
+        return self
+
+    def cuda(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._pack()
+        return self
+
+    def to(self, *args, **kwargs):   # memory_format / dtype arguments of the reference call sites are accepted
+        for a in args:
+            if isinstance(a, (str, torch.device)) and str(a).startswith("cuda"):
+                return self.cuda(torch.device(a).index)
+        return self
+
+    def eval(self):
+        return self
+
+    def share_memory(self):
+        return self
+
+    def _pack(self):
+        sd, dev = self._sd, self.device
+        P = {}
+
+        def conv_bn(prefix_conv, prefix_bn, stride=1):
+            w, b = engine.fold_bn(sd[prefix_conv + ".weight"], sd[prefix_bn + ".weight"], sd[prefix_bn + ".bias"],
+                                  sd[prefix_bn + ".running_mean"], sd[prefix_bn + ".running_var"])
+            return _Conv(w, b, stride, dev)
+
+        def conv_b(prefix, stride=1):
+            return _Conv(sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride, dev)
+
+        block, layers = RESNET_LAYERS[self.backbone]
+        f = "backbones.%s.features." % self.backbone
+        P["stem"] = conv_bn(f + "conv1", f + "bn1", 2)
+        blocks = []
+        for li, nblocks in enumerate(layers):
+            for b in range(nblocks):
+                stride = 2 if (b == 0 and li > 0) else 1
+                p = f + "layer%d.%d." % (li + 1, b)
+                blk = {"level": li + 2, "last": b == nblocks - 1}
+                if block == "bottleneck":
+                    blk["convs"] = [conv_bn(p + "conv1", p + "bn1"), conv_bn(p + "conv2", p + "bn2", stride),
+                                    conv_bn(p + "conv3", p + "bn3")]
+                else:
+                    blk["convs"] = [conv_bn(p + "conv1", p + "bn1", stride), conv_bn(p + "conv2", p + "bn2")]
+                blk["down"] = conv_bn(p + "downsample.0", p + "downsample.1", stride) if (p + "downsample.0.weight") in sd else None
+                blocks.append(blk)
+        P["blocks"] = blocks
+        n = "backbones.%s." % self.backbone
+        for k in ("lateral3", "lateral4", "lateral5", "smooth3", "smooth4", "smooth5"):
+            P[k] = conv_b(n + k)
+        P["pyramid6"] = conv_b(n + "pyramid6", 2)
+        P["pyramid7"] = conv_b(n + "pyramid7", 2)
+        for head in ("cls_head", "box_head"):
+            P[head] = [conv_b("%s.%d" % (head, i)) for i in (0, 2, 4, 6, 8)]
+        self._packed = P
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def _features(self, x):
+        P = self._packed
+        x = P["stem"](x, relu=True)
+        x = engine.maxpool3x3s2(x)
+        outs = {}
+        for blk in P["blocks"]:
+            identity = x if blk["down"] is None else blk["down"](x)
+            cs = blk["convs"]
+            out = x
+            for c in cs[:-1]:
+                out = c(out, relu=True)
+            x = cs[-1](out, relu=True, residual=identity)
+            if blk["last"]:
+                outs[blk["level"]] = x
+        c3, c4, c5 = outs[3], outs[4], outs[5]
+        # FPN (odtk/backbones/fpn.py:45-61)
+        p5 = P["lateral5"](c5)
+        p4 = P["lateral4"](c4, upsample=p5)
+        p3 = P["lateral3"](c3, upsample=p4)
+        p6 = P["pyramid6"](c5)
+        p7 = P["pyramid7"](p6, in_relu=True)
+        return [P["smooth3"](p3), P["smooth4"](p4), P["smooth5"](p5), p6, p7]
+
+    def _heads(self, features, sigmoid=True):
+        P = self._packed
+        cls_heads, box_heads = [], []
+        for t in features:
+            c = t
+            for conv in P["cls_head"][:-1]:
+                c = conv(c, relu=True)
+            cls_heads.append(P["cls_head"][-1](c, out_mode=engine.OUT_NCHW_F32_SIGMOID if sigmoid else engine.OUT_NCHW_F32))
+            b = t
+            for conv in P["box_head"][:-1]:
+                b = conv(b, relu=True)
+            box_heads.append(P["box_head"][-1](b, out_mode=engine.OUT_NCHW_F32))
+        return cls_heads, box_heads
+
+    @staticmethod
+    def _to_nhwc_half(x):
+        if x.dim() != 4:
+            raise ValueError("expected a [B, 3, H, W] batch")
+        return x.permute(0, 2, 3, 1).contiguous().to(torch.float16)   # zero-copy for channels_last fp16
+
+    def forward_heads(self, x, sigmoid=True):
+        """The `exporting=True` view of the reference (odtk/model.py:142-144): per-level
+        (sigmoid) class maps [B, A*C, H, W] and box maps [B, A*4|6, H, W], fp32 NCHW."""
+        if self._packed is None:
+            raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
+        return self._heads(self._features(self._to_nhwc_half(x)), sigmoid)
+
+    def forward(self, x, rotated_bbox=None):
+        cls_heads, box_heads = self.forward_heads(x)
+        if self.exporting:
+            self.strides = [x.shape[-1] // c.shape[-1] for c in cls_heads]
+            return cls_heads, box_heads
+        strides, anchors = [], []
+        for c in cls_heads:
+            stride = x.shape[-1] // c.shape[-1]            # width only (odtk/model.py:155)
+            if stride not in self.anchors:
+                self.anchors[stride] = (box.generate_anchors_rotated(stride, self.ratios, self.scales, self.angles)
+                                        if self.rotated_bbox else box.generate_anchors(stride, self.ratios, self.scales))
+            a = self.anchors[stride][0] if self.rotated_bbox else self.anchors[stride]
+            strides.append(stride)
+            anchors.append(a.reshape(-1).tolist())
+        decoded = _C.decode_levels(cls_heads, box_heads, anchors, strides, self.threshold, self.top_n, self.rotated_bbox)
+        return tuple(_C.nms(*decoded, self.nms, self.detections, self.rotated_bbox))
+
+    __call__ = forward

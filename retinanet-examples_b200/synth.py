@@ -39,3 +39,20 @@ def head_outputs(batch, height=800, width=1280, classes=80, anchors=9, rotated=F
         cls.append(s.to(device))
         box.append(d.to(dtype).to(device))
     return cls, box
+
+
+def calibrate_cls_head(sd, logits_fn, mean=-7.0, std=1.6, seed=0):
+    """Rescale the last class-head convolution of a random-init state_dict so that its logits follow
+    ~N(mean, std^2) (~0.56 % of scores above 0.05, so decode and NMS do
+    representative work; a fresh model yields zero detections).  `logits_fn(state_dict)` must return
+    the per-level raw class logits of some probe batch under these weights (the caller decides
+    how: the GPU engine via Model.forward_heads(sigmoid=False) in the product arm)."""
+    g = torch.Generator().manual_seed(seed)
+    w8 = torch.randn(sd["cls_head.8.weight"].shape, generator=g) * 0.01
+    sd = dict(sd)
+    sd["cls_head.8.weight"], sd["cls_head.8.bias"] = w8, torch.zeros_like(sd["cls_head.8.bias"])
+    flat = torch.cat([l.float().reshape(-1).cpu() for l in logits_fn(sd)])
+    s = std / float(flat.std())
+    sd["cls_head.8.weight"] = w8 * s
+    sd["cls_head.8.bias"] = torch.full_like(sd["cls_head.8.bias"], mean - s * float(flat.mean()))
+    return sd

@@ -1,0 +1,91 @@
+"""GPU parity tests of the full model path (Model.forward on the sm_100a kernels) against the CPU
+oracle (oracle/model_ref.py, pinned to the reference Model by tests/golden/model_*.npz).
+
+Bars.  Convolution stack: fp16 storage / fp32 accumulation vs the fp32 oracle through up to ~55
+layers: |err| <= 3e-2 * max|ref| per head tensor (measured ~5e-3).  Post-processing: bit-exact kept
+indices and scores, coordinates within 1e-3, on IDENTICAL head tensors (ours), which is the
+north_star's parity statement; end-to-end vs the all-fp32 pipeline is reported as a match rate."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref
+from retinanet_examples_b200.model import Model, make_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel_err(got, ref):
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("backbone", ["ResNet18FPN", "ResNet50FPN"])
+def test_heads_match_reference_golden(golden_dir, backbone):
+    g = np.load(os.path.join(golden_dir, "model_%s.npz" % backbone))
+    m = Model(backbone, classes=int(g["classes"]))
+    m.load_state_dict(make_state_dict(backbone, int(g["classes"]), 9, False, int(g["seed"]))).cuda()
+    cls, box = m.forward_heads(torch.from_numpy(g["x"]).to(DEV), sigmoid=True)
+    for i in range(5):
+        assert tuple(cls[i].shape) == g["cls%d" % i].shape
+        assert _rel_err(box[i].cpu(), torch.from_numpy(g["box%d" % i])) < 3e-2, i
+        assert _rel_err(cls[i].cpu(), torch.from_numpy(g["cls%d" % i])) < 3e-2, i
+
+
+@pytest.mark.parametrize("backbone,shape", [("ResNet50FPN", (2, 3, 256, 384)), ("ResNet101FPN", (1, 3, 128, 256)),
+                                            ("ResNet34FPN", (1, 3, 128, 128))])
+def test_heads_match_oracle_logits(backbone, shape):
+    sd = make_state_dict(backbone, 5, 9, False, 3)
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    m = Model(backbone, classes=5).load_state_dict(sd).cuda()
+    cls, box = m.forward_heads(x.to(DEV), sigmoid=False)
+    rc, rb = model_ref.forward_heads(sd, backbone, x, sigmoid=False)
+    for i in range(5):
+        assert _rel_err(cls[i].cpu(), rc[i]) < 3e-2, ("cls", i, _rel_err(cls[i].cpu(), rc[i]))
+        assert _rel_err(box[i].cpu(), rb[i]) < 3e-2, ("box", i, _rel_err(box[i].cpu(), rb[i]))
+
+
+def _spread_head(sd, std=0.05, prior=0.02):
+    """Give the class head some dynamic range so that detections exist (a fresh model has none)."""
+    g = torch.Generator().manual_seed(123)
+    sd = dict(sd)
+    sd["cls_head.8.weight"] = torch.randn(sd["cls_head.8.weight"].shape, generator=g) * std
+    sd["cls_head.8.bias"] = torch.full_like(sd["cls_head.8.bias"], -float(np.log((1 - prior) / prior)))
+    sd["box_head.8.weight"] = torch.randn(sd["box_head.8.weight"].shape, generator=g) * 0.02
+    return sd
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_forward_detections_exact_on_identical_heads(rotated):
+    backbone, classes = "ResNet18FPN", 6
+    na = 27 if rotated else 9
+    sd = _spread_head(make_state_dict(backbone, classes, na, rotated, 9))
+    x = torch.randn((2, 3, 256, 384), generator=torch.Generator().manual_seed(2))
+    m = Model(backbone, classes=classes, rotated_bbox=rotated).load_state_dict(sd).cuda()
+    scores, boxes, cl = [t.cpu().numpy() for t in m(x.to(DEV))]
+    assert (scores > 0).sum() > 20
+    cls_h, box_h = m.forward_heads(x.to(DEV))
+    (os_, ob, oc), _ = model_ref.postprocess([c.cpu() for c in cls_h], [b.cpu() for b in box_h], x.shape[-1],
+                                            rotated=rotated)
+    np.testing.assert_array_equal(scores, os_)
+    np.testing.assert_array_equal(cl, oc)
+    np.testing.assert_allclose(boxes, ob, atol=1e-3, rtol=0)
+
+
+def test_forward_end_to_end_vs_fp32_oracle():
+    backbone, classes = "ResNet18FPN", 6
+    sd = _spread_head(make_state_dict(backbone, classes, 9, False, 10))
+    x = torch.randn((1, 3, 256, 256), generator=torch.Generator().manual_seed(4))
+    m = Model(backbone, classes=classes).load_state_dict(sd).cuda()
+    scores, boxes, cl = [t.cpu().numpy()[0] for t in m(x.to(DEV))]
+    os_, ob, oc = [t[0] for t in model_ref.forward(sd, backbone, x)]
+    n = int(min((scores > 0).sum(), (os_ > 0).sum()))
+    assert n > 10
+    # fp16 conv stack vs fp32: scores agree to ~1e-2 relative; match detections greedily by class + IoU
+    matched = 0
+    for i in range(n):
+        same = (oc[:n] == cl[i]) & (np.abs(ob[:n] - boxes[i]).max(axis=1) < 2.0) & (np.abs(os_[:n] - scores[i]) < 0.02)
+        matched += bool(same.any())
+    assert matched / n > 0.9, matched / n
