@@ -128,12 +128,12 @@ class FullWorkload:
         self.d2h_bytes = batch * self.det * 6 * 4
         self.host_out = torch.empty((batch, self.det, 6), dtype=torch.float32).pin_memory()
         self.out = None
+        self.world_gather = None
         engine.STATS["launches"] = engine.STATS["conv_flops"] = 0
         self.step()
         torch.cuda.synchronize()
         self.launches_per_step = engine.STATS["launches"] + 4       # + decode (3) + nms (1)
         self.flops_per_step = engine.STATS["conv_flops"]
-        self.world_gather = None
 
     def _gather(self, out):
         if self.world_gather:
