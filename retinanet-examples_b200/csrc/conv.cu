@@ -36,7 +36,9 @@ constexpr int kStages = 4;
 constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kBBytesMax = 256 * 128;       // up to 256 rows x 64 fp16
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSlabRowBytes = 128 + 16;       // 64 fp16 + 16 B pad: conflict-free 16-byte accesses
+constexpr int kSlabBytes = 32 * kSlabRowBytes; // per epilogue warp
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * kSlabBytes;
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
@@ -217,78 +219,115 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
+    // One accumulator row (= output pixel) per thread.  NHWC fp16 output goes through a padded
+    // shared-memory staging slab per warp (32 rows x 64 channels) so that global traffic is
+    // row-contiguous: residual / upsample rows are READ coalesced into the slab, combined in fp32
+    // with the accumulator in place, and the slab is WRITTEN back as full 128-byte lines.
     const int q = warp - 4;             // TMEM lane quarter == warp_id % 4
     const int row = q * 32 + lane;      // accumulator row == pixel inside the tile
+    unsigned char *slab = smem + kStages * kStageBytes + 256 + q * kSlabBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
       const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
       const int n0 = n_tile * p.BN;
-      int img, h, w;
-      bool valid;
-      if (p.mode == 1) {
-        const int per_img = p.tiles_h * p.tiles_w;
-        img = m_tile / per_img;
-        const int r = m_tile - img * per_img;
-        h = (r / p.tiles_w) * p.TH + row / p.TW;
-        w = (r % p.tiles_w) * p.TW + row % p.TW;
-        valid = row < p.TH * p.TW && h < p.H && w < p.W;
-      } else {
-        const long long m = (long long)m_tile * 128 + row;
-        valid = m < p.M;
+      // geometry of an arbitrary row of this tile (used for the own row and for slab rows)
+      auto locate = [&](int rr, int &img, int &h, int &w) -> bool {
+        if (p.mode == 1) {
+          const int per_img = p.tiles_h * p.tiles_w;
+          img = m_tile / per_img;
+          const int r = m_tile - img * per_img;
+          h = (r / p.tiles_w) * p.TH + rr / p.TW;
+          w = (r % p.tiles_w) * p.TW + rr % p.TW;
+          return rr < p.TH * p.TW && h < p.H && w < p.W;
+        }
+        const long long m = (long long)m_tile * 128 + rr;
         const int hw = p.H * p.W;
         img = (int)(m / hw);
         const int rem = (int)(m - (long long)img * hw);
         h = rem / p.W;
         w = rem - h * p.W;
-      }
-      const long long pix = ((long long)img * p.H + h) * p.W + w;
+        return m < p.M;
+      };
+      int img, h, w;
+      const bool valid = locate(row, img, h, w);
       mbar_wait(&bars->tmem_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
       const int nchunks = p.BN >> 4;
-      for (int c = 0; c < nchunks; c++) {
-        uint32_t v[16];
-        tc_ld16(taddr + (uint32_t)(c * 16), v);
-        tc_ld_wait();
-        const int col0 = n0 + c * 16;
-        const int ncol = min(16, p.Cout - col0);
-        if (!valid || ncol <= 0) continue;
-        float f[16];
+
+      if (p.out_mode == ODTK_OUT_NHWC_F16) {
+        // slab geometry: 8 lanes x 16 B cover the 64 channels of one row; 4 rows per warp access
+        const int sub = lane >> 3, l8 = lane & 7;
+        int pix8[8], up8[8];   // pixel index (-1: outside) of slab rows sub, 4+sub, ..., 28+sub
 #pragma unroll
-        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; j++) f[j] += (j < ncol) ? __ldg(p.bias + col0 + j) : 0.0f;
+        for (int k = 0; k < 8; k++) {
+          int i2, h2, w2;
+          const bool ok = locate(q * 32 + k * 4 + sub, i2, h2, w2);
+          pix8[k] = ok ? (int)(((long long)i2 * p.H + h2) * p.W + w2) : -1;
+          up8[k] = (ok && p.upsample) ? (int)(((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1)) : -1;
         }
-        if (p.residual && ncol == 16) {
-          const uint4 *r = reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + col0);
-          uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
-          const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0), *h1 = reinterpret_cast<const __half2 *>(&r1);
+        for (int seg = 0; seg * 4 < nchunks; seg++) {
+          const int segc = min(4, nchunks - seg * 4);        // 16-column chunks in this segment
+          const int colbase = n0 + seg * 64;
+          const bool lane_on = l8 * 8 < segc * 16 && colbase + l8 * 8 < p.Cout;
+          // ---- stage residual / upsample rows (coalesced 128-byte reads) ----
+          if (p.residual || p.upsample) {
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+            for (int k = 0; k < 8; k++) {
+              const int r0 = k * 4;
+              const bool ok = pix8[k] >= 0 && lane_on;
+              uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+              if (ok && p.residual) {
+                const long long px = pix8[k];
+                acc = __ldg(reinterpret_cast<const uint4 *>(p.residual + px * p.ldr + colbase + l8 * 8));
+              }
+              if (ok && p.upsample) {
+                const long long up = up8[k];
+                uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.upsample + up * p.Cout + colbase + l8 * 8));
+                if (p.residual) {
+                  __half2 *a2 = reinterpret_cast<__half2 *>(&acc);
+                  const __half2 *u2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                  for (int j = 0; j < 4; j++) a2[j] = __hadd2(a2[j], u2[j]);
+                } else acc = u;
+              }
+              *reinterpret_cast<uint4 *>(slab + (r0 + sub) * kSlabRowBytes + l8 * 16) = acc;
+            }
+            __syncwarp();
           }
-        }
-        if (p.upsample && ncol == 16) {
-          const long long up = ((long long)img * p.up_h + (h >> 1)) * p.up_w + (w >> 1);
-          const uint4 *r = reinterpret_cast<const uint4 *>(p.upsample + up * p.Cout + col0);
-          uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
-          const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0), *h1 = reinterpret_cast<const __half2 *>(&r1);
+          // ---- accumulator (+bias, +staged addend, ReLU) -> fp16 into the own slab row ----
+          for (int cc = 0; cc < segc; cc++) {
+            const int c = seg * 4 + cc;
+            uint32_t v[16];
+            tc_ld16(taddr + (uint32_t)(c * 16), v);
+            tc_ld_wait();
+            const int col0 = n0 + c * 16;
+            float f[16];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-          }
-        }
-        if (p.relu) {
+            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
+            if (p.bias && col0 < p.Cout) {
+              const float4 *bp = reinterpret_cast<const float4 *>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.0f);
-        }
-        if (p.out_mode == ODTK_OUT_NHWC_F16) {
-          __half *o = reinterpret_cast<__half *>(p.out) + pix * p.ldy + col0;
-          if (ncol == 16) {
+              for (int j = 0; j < 4; j++) {
+                float4 b4 = __ldg(bp + j);
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+              }
+            }
+            uint4 *srow = reinterpret_cast<uint4 *>(slab + lane * kSlabRowBytes + cc * 32);
+            if (p.residual || p.upsample) {
+              uint4 r0 = srow[0], r1 = srow[1];
+              const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0), *h1 = reinterpret_cast<const __half2 *>(&r1);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.0f);
+            }
             uint4 o0, o1;
             __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
 #pragma unroll
@@ -296,20 +335,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
               q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
             }
-            reinterpret_cast<uint4 *>(o)[0] = o0;
-            reinterpret_cast<uint4 *>(o)[1] = o1;
-          } else {
-            for (int j = 0; j < ncol; j++) o[j] = __float2half_rn(f[j]);
+            srow[0] = o0;
+            srow[1] = o1;
           }
-        } else {
-          // fp32 NCHW (+ sigmoid): lanes of a warp are consecutive pixels of a row -> coalesced
-          float *o = reinterpret_cast<float *>(p.out) + ((long long)img * p.Cout + col0) * ((long long)p.H * p.W) +
-                     (long long)h * p.W + w;
-          const long long cs = (long long)p.H * p.W;
+          __syncwarp();
+          // ---- slab -> global, 4 rows x 128 contiguous bytes per warp store ----
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int r0 = k * 4;
+            if (pix8[k] >= 0 && lane_on) {
+              const long long px = pix8[k];
+              uint4 val = *reinterpret_cast<const uint4 *>(slab + (r0 + sub) * kSlabRowBytes + l8 * 16);
+              *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + px * p.ldy + colbase + l8 * 8) = val;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // fp32 NCHW (+ sigmoid): lanes of a warp are consecutive pixels of a row -> coalesced
+        const long long cs = (long long)p.H * p.W;
+        for (int c = 0; c < nchunks; c++) {
+          uint32_t v[16];
+          tc_ld16(taddr + (uint32_t)(c * 16), v);
+          tc_ld_wait();
+          const int col0 = n0 + c * 16;
+          const int ncol = min(16, p.Cout - col0);
+          if (!valid || ncol <= 0) continue;
+          float *o = reinterpret_cast<float *>(p.out) + ((long long)img * p.Cout + col0) * cs + (long long)h * p.W + w;
 #pragma unroll
           for (int j = 0; j < 16; j++) {
             if (j < ncol) {
-              float x = f[j];
+              float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.0f);
+              if (p.relu) x = fmaxf(x, 0.0f);
               if (p.out_mode == ODTK_OUT_NCHW_F32_SIGMOID) x = sigmoidf_accurate(x);
               o[j * cs] = x;
             }
@@ -387,6 +444,9 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (d->ksize != 1 && d->ksize != 3) return ODTK_E_UNSUPPORTED;
   if (d->cin % 64 != 0) return ODTK_E_UNSUPPORTED;  // 64-channel K blocks (128-byte swizzle rows)
   if (d->out_mode < 0 || d->out_mode > 2) return ODTK_E_INVALID;
+  if (d->out_mode == ODTK_OUT_NHWC_F16 && (d->cout % 16)) return ODTK_E_UNSUPPORTED;
+  if (d->out_mode != ODTK_OUT_NHWC_F16 && (d->residual || d->upsample)) return ODTK_E_UNSUPPORTED;
+  if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
   if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y) & 15) return ODTK_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!g_num_sms) {
