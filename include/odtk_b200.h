@@ -145,8 +145,29 @@ int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
  * relu != 0 applies ReLU to the gathered values: FPN pyramid7 input, fpn.py:55).     */
 int odtk_lower_conv(const void *x, void *out, int n, int h, int w, int c, int ksize, int stride, int pad,
                     int kpad, int relu, odtk_stream_t stream);
+/* ResNet stem (7x7 stride-2 pad-3 conv of the RGB image) without im2col: odtk_pad_input
+ * zero-pads NHWC3 fp16 [n,h,w,3] to NHWC4 [n,h+6,w+8,4]; odtk_stem_conv runs the tensor-core
+ * kernel over an overlapping-window tensor map of that buffer.  w: fp16 [cout, 7*32] with
+ * k = r*32 + s*4 + c (zero for s = 7, c = 3); y: NHWC fp16 [n, h/2, w/2, cout]; h, w even.   */
+int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_stream_t stream);
+int odtk_stem_conv(const void *xp, const void *w, const float *bias, void *y, int n, int h, int width,
+                   int cout, int relu, odtk_stream_t stream);
 /* 3x3 stride-2 pad-1 max-pool, NHWC fp16 (torchvision resnet stem).                  */
 int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, int c, odtk_stream_t stream);
+
+/* ---- focal loss (training path) -------------------------------------------------------
+ * Replaces FocalLoss.forward (odtk/loss.py:13-18) + the mask / sum of
+ * Model._compute_loss (odtk/model.py:195-199) and its autograd backward, in ONE pass:
+ *   loss_i = mask_i * alpha_t * (1 - p_t)^gamma * BCEwithLogits(x_i, t_i)
+ *   *loss_sum = sum_i loss_i;  grad_i = grad_scale * d(loss_sum)/dx_i
+ * Targets: dense fp32 one-hot `target` [n] (+ optional dense `mask` [n]), the reference's
+ * layout; or `cls_index` int32 [n / (num_classes*hw), hw] with the class id per anchor
+ * position (-1 background, -2 ignored => mask 0) for logits laid out [group, class, hw].
+ * loss_elem (per-element loss, [n]) and grad ([n]) may be NULL.  Two-phase workspace.  */
+long long odtk_focal_loss(const float *logits, const float *target, const float *mask, const int *cls_index,
+                          long long n, int num_classes, int hw, float alpha, float gamma, float grad_scale,
+                          float *loss_elem, float *loss_sum, float *grad, void *workspace,
+                          size_t workspace_size, odtk_stream_t stream);
 
 /* ---- per-kernel timing (B200-native addition; the reference has only a wall-clock
  * Profiler without CUDA sync, odtk/utils.py:140-167) ------------------------------

@@ -32,14 +32,18 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
+constexpr int kPipeBytes = 4 * (128 * 128 + 256 * 128);   // pipeline region: 4 stages at BN = 256, up to 8 at small BN
+#ifndef ODTK_EPI_WARPS
+#define ODTK_EPI_WARPS 8   /* measured on B200: 8 warps (168 regs, no spills) 1137 img/s vs 16 warps (96 regs, spills) 961 */
+#endif
+constexpr int kEpiWarps = ODTK_EPI_WARPS;                 // 4 per TMEM lane quarter; each takes every 4th 64-column segment
 constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kBBytesMax = 256 * 128;       // up to 256 rows x 64 fp16
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSlabRowBytes = 128 + 16;       // 64 fp16 + 16 B pad: conflict-free 16-byte accesses
+constexpr int kSlabRowBytes = 128;            // 64 fp16, no padding: 16-byte units are XOR-swizzled with (row & 7)
 constexpr int kSlabBytes = 32 * kSlabRowBytes; // per epilogue warp
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * kSlabBytes;
-constexpr int kThreads = 256;
+constexpr int kSmemBytes = kPipeBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kSlabBytes;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
 
@@ -80,6 +84,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -106,25 +117,29 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 64 fp16 = 128 B, 8-row
 // groups 1024 B apart (SBO), LBO unused for swizzled K-major layouts, descriptor version 1.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+// `row_bytes` = 128 (SWIZZLE_128B, layout type 2) or 64 (SWIZZLE_64B, layout type 4): the 8-row
+// swizzle atom is 8 * row_bytes.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, int row_bytes) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
-  d |= (uint64_t)1 << 16;                      // LBO (ignored)  [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;            // SBO = 1024 B   [32,46)
-  d |= (uint64_t)1 << 46;                      // version = 1    [46,48)
-  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B   [61,64)
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address  [0,14)
+  d |= (uint64_t)1 << 16;                              // LBO (ignored)  [16,30)
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;         // SBO            [32,46)
+  d |= (uint64_t)1 << 46;                              // version = 1    [46,48)
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;     // swizzle mode   [61,64)
   return d;
 }
 
 struct Barriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float sigmoidf_accurate(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid with the SFU approximations (ex2.approx + rcp.approx): relative error < 1e-6, far inside
+// the 1e-3 score tolerance, and ~4x fewer instructions than expf + IEEE division in a hot epilogue
+__device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreads, 1)
@@ -132,7 +147,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ ConvParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Barriers *bars = reinterpret_cast<Barriers *>(smem + kStages * kStageBytes);
+  Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes);
+  const int kStages = p.nstages, kStageBytes = kABytes + p.BN * 128;   // per-layer pipeline geometry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -141,7 +157,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 128); }
+    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -156,8 +172,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.taps * p.kblocks_per_tap;
-  const uint32_t a_bytes = (p.mode == 1) ? (uint32_t)(p.TH * p.TW * 128) : (uint32_t)kABytes;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t a_bytes = (p.mode == 0) ? (uint32_t)(128 * p.row_bytes) : (uint32_t)(p.TH * p.TW * p.row_bytes);
+  const uint32_t b_bytes = (uint32_t)(p.BN * p.row_bytes);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -168,7 +184,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
         const int n0 = n_tile * p.BN;
         int img = 0, h0 = 0, w0 = 0;
-        if (p.mode == 1) {
+        if (p.mode != 0) {
           const int per_img = p.tiles_h * p.tiles_w;
           img = m_tile / per_img;
           const int r = m_tile - img * per_img;
@@ -182,9 +198,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             unsigned char *sa = smem + stage * kStageBytes;
             unsigned char *sb = sa + kABytes;
             mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
-            if (p.mode == 1) tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
-            else             tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
-            tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * 64, n0);
+            const int kelems = p.row_bytes >> 1;   // K elements per block: 64 (SW128) or 32 (SW64)
+            if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
+            else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
+            else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
+            tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -207,9 +225,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < 4; k++)  // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the swizzle atom
+          const uint64_t da = make_desc_kmajor(sa, p.row_bytes), db = make_desc_kmajor(sa + kABytes, p.row_bytes);
+          const int ksteps = p.row_bytes >> 5;   // UMMA_K(16) steps per block: +32 B each inside the swizzle atom
+          for (int k = 0; k < ksteps; k++)
             tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -219,142 +237,173 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    // One accumulator row (= output pixel) per thread.  NHWC fp16 output goes through a padded
-    // shared-memory staging slab per warp (32 rows x 64 channels) so that global traffic is
-    // row-contiguous: residual / upsample rows are READ coalesced into the slab, combined in fp32
-    // with the accumulator in place, and the slab is WRITTEN back as full 128-byte lines.
-    const int q = warp - 4;             // TMEM lane quarter == warp_id % 4
+    // 16 warps: warp_id % 4 selects the TMEM lane quarter (hardware rule), (warp_id - 4) / 4 selects
+    // which column segments of the tile the warp owns.  One accumulator row (= output pixel) per
+    // thread.  NHWC fp16 output goes through a padded shared-memory slab per warp so that global
+    // traffic is row-contiguous: residual / upsample rows are READ coalesced into the slab (all
+    // loads of a segment issued back to back, one segment ahead), combined in fp32 with the
+    // accumulator in place, and the slab is WRITTEN back as contiguous row pieces.
+    // Everything that does not depend on the tile is computed once, outside the tile loop.
+    const int q = warp & 3;
+    const int sg = (warp - 4) >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel inside the tile
-    unsigned char *slab = smem + kStages * kStageBytes + 256 + q * kSlabBytes;
+    unsigned char *slab = smem + kPipeBytes + 256 + (warp - 4) * kSlabBytes;
+    const int nchunks = p.BN >> 4;
+    // column split: 4 segments of cpw 16-column chunks (cpw = 1, 2, 4 for BN <= 64, 128, 256);
+    // a slab row holds cpw*32 bytes = lpr lanes x 16 B and one warp access covers 32/lpr rows
+    const int cpw = nchunks <= 4 ? 1 : (nchunks <= 8 ? 2 : 4);
+    const int lsh = cpw == 1 ? 1 : (cpw == 2 ? 2 : 3);
+    const int lpr = 1 << lsh, rpi = 32 >> lsh;
+    const int sub = lane >> lsh, lx = lane & (lpr - 1);
+    const int nsegs = (nchunks + cpw - 1) / cpw;
+    const bool nhwc = p.out_mode == ODTK_OUT_NHWC_F16;
+    const bool has_addend = p.residual != nullptr || p.upsample != nullptr;
+    const int hw = p.H * p.W, per_img = p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
+    // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
+    int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
+    if (p.mode != 0) { own_dh = row / p.TW; own_dw = row - own_dh * p.TW; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int rr = q * 32 + k * rpi + sub;
+      dh8[k] = (p.mode != 0) ? rr / p.TW : 0;
+      dw8[k] = (p.mode != 0) ? rr - dh8[k] * p.TW : rr;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
       const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
       const int n0 = n_tile * p.BN;
-      // geometry of an arbitrary row of this tile (used for the own row and for slab rows)
-      auto locate = [&](int rr, int &img, int &h, int &w) -> bool {
-        if (p.mode == 1) {
-          const int per_img = p.tiles_h * p.tiles_w;
-          img = m_tile / per_img;
-          const int r = m_tile - img * per_img;
-          h = (r / p.tiles_w) * p.TH + rr / p.TW;
-          w = (r % p.tiles_w) * p.TW + rr % p.TW;
-          return rr < p.TH * p.TW && h < p.H && w < p.W;
-        }
-        const long long m = (long long)m_tile * 128 + rr;
-        const int hw = p.H * p.W;
-        img = (int)(m / hw);
-        const int rem = (int)(m - (long long)img * hw);
-        h = rem / p.W;
-        w = rem - h * p.W;
-        return m < p.M;
-      };
-      int img, h, w;
-      const bool valid = locate(row, img, h, w);
+      const bool active = nhwc ? (sg < nsegs) : (sg < nchunks);
       mbar_wait(&bars->tmem_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
-      const int nchunks = p.BN >> 4;
-
-      if (p.out_mode == ODTK_OUT_NHWC_F16) {
-        // slab geometry: 8 lanes x 16 B cover the 64 channels of one row; 4 rows per warp access
-        const int sub = lane >> 3, l8 = lane & 7;
-        int pix8[8], up8[8];   // pixel index (-1: outside) of slab rows sub, 4+sub, ..., 28+sub
+      // warp-uniform tile origin
+      int img0 = 0, h0 = 0, w0 = 0;
+      if (p.mode != 0) {
+        img0 = m_tile / per_img;
+        const int r = m_tile - img0 * per_img;
+        h0 = (r / p.tiles_w) * p.TH;
+        w0 = (r % p.tiles_w) * p.TW;
+      }
+      if (active && nhwc) {
+        int pix8[8];   // pixel index (-1: outside the tensor) of slab rows sub, rpi+sub, ...
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          int i2, h2, w2;
-          const bool ok = locate(q * 32 + k * 4 + sub, i2, h2, w2);
-          pix8[k] = ok ? (int)(((long long)i2 * p.H + h2) * p.W + w2) : -1;
-          up8[k] = (ok && p.upsample) ? (int)(((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1)) : -1;
+          if (p.mode != 0) {
+            const int rr = q * 32 + k * rpi + sub, h = h0 + dh8[k], w = w0 + dw8[k];
+            pix8[k] = (k < lpr && rr < patch && h < p.H && w < p.W) ? (img0 * p.H + h) * p.W + w : -1;
+          } else {
+            const int m = m_tile * 128 + dw8[k];
+            pix8[k] = (k < lpr && (long long)m < p.M) ? m : -1;
+          }
         }
-        for (int seg = 0; seg * 4 < nchunks; seg++) {
-          const int segc = min(4, nchunks - seg * 4);        // 16-column chunks in this segment
-          const int colbase = n0 + seg * 64;
-          const bool lane_on = l8 * 8 < segc * 16 && colbase + l8 * 8 < p.Cout;
-          // ---- stage residual / upsample rows (coalesced 128-byte reads) ----
-          if (p.residual || p.upsample) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const int r0 = k * 4;
-              const bool ok = pix8[k] >= 0 && lane_on;
-              uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-              if (ok && p.residual) {
-                const long long px = pix8[k];
-                acc = __ldg(reinterpret_cast<const uint4 *>(p.residual + px * p.ldr + colbase + l8 * 8));
-              }
-              if (ok && p.upsample) {
-                const long long up = up8[k];
-                uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.upsample + up * p.Cout + colbase + l8 * 8));
-                if (p.residual) {
-                  __half2 *a2 = reinterpret_cast<__half2 *>(&acc);
-                  const __half2 *u2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                  for (int j = 0; j < 4; j++) a2[j] = __hadd2(a2[j], u2[j]);
-                } else acc = u;
-              }
-              *reinterpret_cast<uint4 *>(slab + (r0 + sub) * kSlabRowBytes + l8 * 16) = acc;
-            }
-            __syncwarp();
-          }
-          // ---- accumulator (+bias, +staged addend, ReLU) -> fp16 into the own slab row ----
-          for (int cc = 0; cc < segc; cc++) {
-            const int c = seg * 4 + cc;
-            uint32_t v[16];
-            tc_ld16(taddr + (uint32_t)(c * 16), v);
-            tc_ld_wait();
-            const int col0 = n0 + c * 16;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
-            if (p.bias && col0 < p.Cout) {
-              const float4 *bp = reinterpret_cast<const float4 *>(p.bias + col0);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float4 b4 = __ldg(bp + j);
-                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-              }
-            }
-            uint4 *srow = reinterpret_cast<uint4 *>(slab + lane * kSlabRowBytes + cc * 32);
-            if (p.residual || p.upsample) {
-              uint4 r0 = srow[0], r1 = srow[1];
-              const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0), *h1 = reinterpret_cast<const __half2 *>(&r1);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-                f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.0f);
-            }
-            uint4 o0, o1;
-            __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-              q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-            }
-            srow[0] = o0;
-            srow[1] = o1;
-          }
-          __syncwarp();
-          // ---- slab -> global, 4 rows x 128 contiguous bytes per warp store ----
+        auto fetch = [&](int seg, uint4 (&dst)[8]) {
+          const int colbase = n0 + seg * cpw * 16 + lx * 8;
+          const bool lane_on = lx * 8 < min(cpw, nchunks - seg * cpw) * 16 && colbase < p.Cout;
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            const int r0 = k * 4;
+            dst[k] = make_uint4(0u, 0u, 0u, 0u);
             if (pix8[k] >= 0 && lane_on) {
-              const long long px = pix8[k];
-              uint4 val = *reinterpret_cast<const uint4 *>(slab + (r0 + sub) * kSlabRowBytes + l8 * 16);
-              *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + px * p.ldy + colbase + l8 * 8) = val;
+              if (p.residual) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
+              if (p.upsample) {
+                const int i2 = pix8[k] / hw, rem = pix8[k] - i2 * hw, h2 = rem / p.W, w2 = rem - h2 * p.W;
+                const long long up = ((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1);
+                uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.upsample + up * p.Cout + colbase));
+                __half2 *a2 = reinterpret_cast<__half2 *>(&dst[k]);
+                const __half2 *u2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; j++) a2[j] = __hadd2(a2[j], u2[j]);
+              }
+            }
+          }
+        };
+        uint4 pre[8];
+        if (has_addend) fetch(sg, pre);
+        for (int seg = sg; seg < nsegs; seg += kEpiWarps / 4) {
+          const int segc = min(cpw, nchunks - seg * cpw);      // 16-column chunks in this segment
+          const int colbase = n0 + seg * cpw * 16;
+          const bool lane_on = lx * 8 < segc * 16 && colbase + lx * 8 < p.Cout;
+          if (has_addend) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              if (k < lpr) *reinterpret_cast<uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)) = pre[k];
+            __syncwarp();
+            if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, pre);
+          }
+          // ---- accumulator (+bias, +staged addend, ReLU) -> fp16 into the own slab row ----
+          uint32_t v[2][16];
+          tc_ld16(taddr + (uint32_t)(seg * cpw * 16), v[0]);
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) {
+            if (cc < segc) {
+              tc_ld_wait();
+              if (cc + 1 < segc) tc_ld16(taddr + (uint32_t)((seg * cpw + cc + 1) * 16), v[(cc + 1) & 1]);
+              const int col0 = colbase + cc * 16;
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[cc & 1][j]);
+              if (p.bias && col0 < p.Cout) {
+                const float4 *bp = reinterpret_cast<const float4 *>(p.bias + col0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  float4 b4 = __ldg(bp + j);
+                  f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                }
+              }
+              unsigned char *srow = slab + lane * kSlabRowBytes;
+              const int u0 = ((2 * cc) ^ (lane & 7)) << 4, u1 = u0 ^ 16;
+              if (has_addend) {
+                uint4 r0 = *reinterpret_cast<uint4 *>(srow + u0), r1 = *reinterpret_cast<uint4 *>(srow + u1);
+                const __half2 *x0 = reinterpret_cast<const __half2 *>(&r0), *x1 = reinterpret_cast<const __half2 *>(&r1);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  float2 a = __half22float2(x0[j]), b = __half22float2(x1[j]);
+                  f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4 o0, o1;
+              __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+              }
+              *reinterpret_cast<uint4 *>(srow + u0) = o0;
+              *reinterpret_cast<uint4 *>(srow + u1) = o1;
+            }
+          }
+          __syncwarp();
+          // ---- slab -> global: rpi rows x (lpr x 16) contiguous bytes per warp store ----
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            if (k < lpr && pix8[k] >= 0 && lane_on) {
+              uint4 val = *reinterpret_cast<const uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4));
+              *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + (long long)pix8[k] * p.ldy + colbase + lx * 8) = val;
             }
           }
           __syncwarp();
         }
-      } else {
+      } else if (active) {
         // fp32 NCHW (+ sigmoid): lanes of a warp are consecutive pixels of a row -> coalesced
-        const long long cs = (long long)p.H * p.W;
-        for (int c = 0; c < nchunks; c++) {
+        int img, h, w;
+        bool valid;
+        if (p.mode != 0) {
+          img = img0; h = h0 + own_dh; w = w0 + own_dw;
+          valid = row < patch && h < p.H && w < p.W;
+        } else {
+          const int m = m_tile * 128 + row;
+          valid = (long long)m < p.M;
+          img = m / hw;
+          const int rem = m - img * hw;
+          h = rem / p.W;
+          w = rem - h * p.W;
+        }
+        const long long cs = hw;
+        for (int c = sg; c < nchunks; c += kEpiWarps / 4) {
           uint32_t v[16];
           tc_ld16(taddr + (uint32_t)(c * 16), v);
           tc_ld_wait();
@@ -405,7 +454,7 @@ EncodeTiledFn get_encode() {
 }
 
 bool encode_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                const uint32_t *box) {
+                const uint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return false;
   cuuint64_t gdim[5], gstr[5];
@@ -413,7 +462,7 @@ bool encode_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims
   for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -461,6 +510,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   p.N = d->n; p.H = d->h; p.W = d->width; p.Cin = d->cin; p.Cout = d->cout;
   p.kw = d->ksize; p.taps = d->ksize * d->ksize; p.pad = d->ksize / 2;
   p.kblocks_per_tap = d->cin / 64;
+  p.row_bytes = 128;
   p.M = (long long)d->n * d->h * d->width;
   // N tile: whole Cout when it fits 256 columns, else the largest multiple-of-16 divisor-ish tile
   int BN;
@@ -470,6 +520,8 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     BN = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
   }
   p.BN = BN;
+  p.nstages = kPipeBytes / (kABytes + BN * 128);
+  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
   p.num_n_tiles = (d->cout + BN - 1) / BN;
   p.bias = d->bias;
   p.residual = (const __half *)d->residual;
@@ -510,6 +562,65 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  {
+    OdtkProfScope prof(ODTK_PROF_CONV, stream);
+    conv_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+// ResNet stem: 7x7 stride-2 pad-3 convolution of the RGB image, im2col-free.  `xp` is the image
+// zero-padded to NHWC4 [n, h+6, w+8, 4] fp16 by odtk_pad_input.  For filter row r the A operand of
+// output pixels (oh, ow..) is the 8-pixel x 4-channel window starting at padded pixel (2*oh + r, 2*ow):
+// 64 contiguous bytes, consecutive output pixels 16 bytes apart -- an OVERLAPPING-window 5-D tensor map
+// {32 elements, OW (16 B), 7 rows (one padded row), OH (two padded rows), N}.  K = 7 blocks of 32
+// (SWIZZLE_64B), weights packed [64, 7*32] with k = r*32 + s*4 + c (zero for s = 7 or c = 3).
+extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, void *y, int n, int h, int width,
+                              int cout, int relu, odtk_stream_t stream_) {
+  if (!xp || !w || !y || n <= 0 || h <= 0 || width <= 0) return ODTK_E_INVALID;
+  if ((h & 1) || (width & 1) || cout % 16 || cout > 256) return ODTK_E_UNSUPPORTED;
+  if (((uintptr_t)xp | (uintptr_t)w | (uintptr_t)y) & 15) return ODTK_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+      return ODTK_E_CUDA;
+  }
+  const int OH = h / 2, OW = width / 2, HP = h + 6, WP = width + 8;
+  if ((long long)n * OH * OW >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
+  ConvParams p;
+  memset(&p, 0, sizeof p);
+  p.mode = 2;
+  p.N = n; p.H = OH; p.W = OW; p.Cin = 4; p.Cout = cout;
+  p.kw = 1; p.taps = 7; p.pad = 0; p.kblocks_per_tap = 1;
+  p.row_bytes = 64;
+  p.M = (long long)n * OH * OW;
+  p.BN = cout;
+  p.num_n_tiles = 1;
+  p.nstages = kPipeBytes / (kABytes + p.BN * 128);
+  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+  p.bias = bias; p.out = y; p.relu = relu; p.out_mode = ODTK_OUT_NHWC_F16; p.ldy = cout; p.ldr = cout;
+  choose_patch(OH, OW, p.TH, p.TW);
+  p.tiles_h = (OH + p.TH - 1) / p.TH;
+  p.tiles_w = (OW + p.TW - 1) / p.TW;
+  p.num_m_tiles = n * p.tiles_h * p.tiles_w;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {32, (uint64_t)OW, 7, (uint64_t)OH, (uint64_t)n};
+    uint64_t str[4] = {16, (uint64_t)WP * 8, (uint64_t)WP * 16, (uint64_t)HP * WP * 8};
+    uint32_t box[5] = {32, (uint32_t)p.TW, 1, (uint32_t)p.TH, 1};
+    if (!encode_map(&tmA, xp, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return ODTK_E_UNSUPPORTED;
+  }
+  {
+    uint64_t dims[2] = {224, (uint64_t)cout};
+    uint64_t str[1] = {224 * 2};
+    uint32_t box[2] = {32, (uint32_t)cout};
+    if (!encode_map(&tmB, w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return ODTK_E_CUDA;
+  }
+  const int total = p.num_m_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);

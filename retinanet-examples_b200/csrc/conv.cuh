@@ -3,7 +3,8 @@
 #include <cuda_fp16.h>
 
 struct ConvParams {
-  int mode;             // 0: rows of a [M, Cin] matrix (1x1 conv / lowered conv); 1: spatial patches (3x3, pad 1)
+  int mode;             // 0: rows of a [M, Cin] matrix (1x1 / lowered conv); 1: spatial patches (3x3, pad 1);
+                        // 2: 7x7 stride-2 stem over a zero-padded NHWC4 image (overlapping-window 5-D map)
   int N, H, W, Cin, Cout;
   int taps, kw, pad;    // 1 / 9 taps
   int TH, TW, tiles_h, tiles_w;   // mode 1: patch and patches per image
@@ -14,4 +15,6 @@ struct ConvParams {
   const __half *upsample;  // NHWC fp16 [N, H/2, W/2, Cout] (FPN top-down path) or NULL
   void *out;
   int relu, out_mode, ldy, ldr, up_h, up_w;
+  int row_bytes;        // bytes of one K block row in shared memory: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, stem)
+  int nstages;          // pipeline stages that fit: (16 KB + BN*128 B) each
 };

@@ -102,6 +102,27 @@ __global__ void maxpool3x3s2_kernel(const __half *__restrict__ x, __half *__rest
   }
 }
 
+// RGB NHWC3 fp16 -> zero-padded NHWC4 [n, h+6, w+8, 4]: 3 rows/columns of zeros before, 3/5 after
+// (the stem's overlapping-window tensor map never leaves the buffer).  One 8-byte pixel per thread.
+__global__ void pad_input_kernel(const __half *__restrict__ x, __half *__restrict__ y, int N, int H, int W) {
+  const int HP = H + 6, WP = W + 8;
+  const long long total = (long long)N * HP * WP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int xp = (int)(i % WP);
+    long long t = i / WP;
+    int yp = (int)(t % HP);
+    int n = (int)(t / HP);
+    int ih = yp - 3, iw = xp - 3;
+    uint2 v = make_uint2(0u, 0u);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const unsigned short *s = reinterpret_cast<const unsigned short *>(x) + (((long long)n * H + ih) * W + iw) * 3;
+      v.x = (unsigned)s[0] | ((unsigned)s[1] << 16);
+      v.y = (unsigned)s[2];
+    }
+    reinterpret_cast<uint2 *>(y)[i] = v;
+  }
+}
+
 inline int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = 148ll * 16;
@@ -136,5 +157,12 @@ extern "C" int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, in
   long long total = (long long)n * oh * ow * (c / 8);
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w,
                                                                                c, oh, ow);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_stream_t stream_) {
+  if (!x || !y || n <= 0 || h <= 0 || w <= 0) return ODTK_E_INVALID;
+  long long total = (long long)n * (h + 6) * (w + 8);
+  pad_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

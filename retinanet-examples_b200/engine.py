@@ -84,3 +84,29 @@ def maxpool3x3s2(x):
                                             _stream()), "maxpool3x3s2")
     STATS["launches"] += 1
     return out
+
+
+def pack_stem_weight(weight):
+    """[Cout, 3, 7, 7] fp32 -> [Cout, 7*32] fp16 with k = r*32 + s*4 + c (zero for s = 7 or c = 3):
+    the K order of the stem's overlapping-window tensor map (odtk_stem_conv)."""
+    cout = weight.shape[0]
+    w = weight.new_zeros((cout, 7, 8, 4))
+    w[:, :, :7, :3] = weight.permute(0, 2, 3, 1)          # [cout, r, s, c]
+    return w.reshape(cout, 224).to(torch.float16).contiguous()
+
+
+def stem_conv(x, w, bias, cout, relu=True):
+    """7x7 stride-2 pad-3 convolution of an NHWC fp16 RGB batch [N,H,W,3] on the tensor cores:
+    zero-pad to NHWC4 (one small kernel), then the conv kernel in stem mode.  Returns
+    NHWC fp16 [N, H/2, W/2, cout]."""
+    n, h, wd, c = x.shape
+    assert c == 3 and x.dtype == torch.float16 and x.is_contiguous()
+    xp = torch.empty((n, h + 6, wd + 8, 4), dtype=torch.float16, device=x.device)
+    L = _lib.lib()
+    _lib.check(L.odtk_pad_input(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, wd, _stream()), "pad_input")
+    out = torch.empty((n, h // 2, wd // 2, cout), dtype=torch.float16, device=x.device)
+    _lib.check(L.odtk_stem_conv(ctypes.c_void_p(xp.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+                                ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                ctypes.c_void_p(out.data_ptr()), n, h, wd, cout, int(relu), _stream()), "stem_conv")
+    STATS["launches"] += 2
+    return out

@@ -1,0 +1,70 @@
+"""Host-side mirror of the reference's odtk/loss.py FocalLoss on the fused sm_100a kernel
+(odtk_focal_loss in include/odtk_b200.h).  `FocalLoss()(pred_logits, target)` returns the
+element-wise loss like the reference module; `focal_loss_sum` is the fused training form
+(masked sum + gradient in one pass, usable with autograd)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _launch(logits, target, mask, cls_index, num_classes, hw, alpha, gamma, grad_scale, want_elem, want_grad):
+    if not logits.is_cuda:
+        raise RuntimeError("pred_logits must be a CUDA tensor")
+    L = _lib.lib()
+    x = logits.float().contiguous()
+    n = x.numel()
+    elem = torch.empty_like(x) if want_elem else None
+    grad = torch.empty_like(x) if want_grad else None
+    total = torch.empty(1, dtype=torch.float32, device=x.device)
+
+    def p(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    args = (p(x), p(target), p(mask), p(cls_index), n, int(num_classes), int(hw), float(alpha), float(gamma),
+            float(grad_scale), p(elem), p(total), p(grad))
+    size = _lib.check(L.odtk_focal_loss(*args, None, 0, None), "focal_loss (workspace query)")
+    ws = torch.empty(int(size), dtype=torch.uint8, device=x.device)
+    _lib.check(L.odtk_focal_loss(*args, ctypes.c_void_p(ws.data_ptr()), size,
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "focal_loss")
+    return total, elem, grad
+
+
+class FocalLoss:
+    'Focal Loss - https://arxiv.org/abs/1708.02002 (reference: odtk/loss.py:5-18)'
+
+    def __init__(self, alpha=0.25, gamma=2):
+        self.alpha, self.gamma = alpha, gamma
+
+    def forward(self, pred_logits, target):
+        t = target.float().contiguous()
+        _, elem, _ = _launch(pred_logits, t, None, None, 0, 0, self.alpha, self.gamma, 1.0, True, False)
+        return elem.view_as(pred_logits)
+
+    __call__ = forward
+
+
+class _FocalSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, mask, cls_index, num_classes, hw, alpha, gamma):
+        total, _, grad = _launch(logits, target, mask, cls_index, num_classes, hw, alpha, gamma, 1.0, False, True)
+        ctx.save_for_backward(grad.view_as(logits))
+        return total[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None, None, None
+
+
+def focal_loss_sum(pred_logits, target=None, mask=None, cls_index=None, alpha=0.25, gamma=2.0):
+    """sum(mask * FocalLoss(pred_logits, target)) with the gradient produced in the same pass
+    (== `(cls_mask * cls_criterion(cls_head, cls_target)).sum()`, odtk/model.py:196-199).
+    Either a dense one-hot `target` (+ optional dense `mask`) or `cls_index` int32 [groups, H*W]
+    for logits shaped [groups, classes, H*W] (-1 background, -2 ignored)."""
+    if cls_index is not None:
+        ncls, hw = pred_logits.shape[-2], pred_logits.shape[-1]
+        return _FocalSum.apply(pred_logits, None, None, cls_index.int().contiguous(), ncls, hw, alpha, gamma)
+    t = target.float().contiguous()
+    m = mask.float().expand_as(t).contiguous() if mask is not None else None
+    return _FocalSum.apply(pred_logits, t, m, None, 0, 0, alpha, gamma)

@@ -94,6 +94,8 @@ class _Conv:
         cout, cin, kh, kw = weight.shape
         self.cout, self.cin, self.ks, self.stride = cout, cin, kh, stride
         self.direct = stride == 1 and kh in (1, 3) and cin % 64 == 0
+        self.stem = (cin == 3 and kh == 7 and stride == 2 and cout % 16 == 0 and cout <= 256)
+        self.w_stem = engine.pack_stem_weight(weight).to(device) if self.stem else None
         kreal = kh * kw * cin
         self.kpad = kreal if self.direct else (kreal + 63) // 64 * 64
         self.w = engine.pack_weight(weight, self.kpad).to(device)
@@ -102,6 +104,8 @@ class _Conv:
     def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False):
         oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
         engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin
+        if self.stem and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and residual is None and upsample is None:
+            return engine.stem_conv(x, self.w_stem, self.b, self.cout, relu)
         if self.direct:
             assert not in_relu
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode)

@@ -108,3 +108,12 @@ def test_maxpool_matches_torch():
     y = engine.maxpool3x3s2(x.to(DEV))
     ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
     np.testing.assert_array_equal(y.float().cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 32, 64), (2, 128, 256), (1, 226, 130)])
+def test_stem_conv_overlapping_window_tma(n, h, w):
+    """7x7 stride-2 stem through the zero-padded NHWC4 image + overlapping-window tensor map."""
+    g = torch.Generator().manual_seed(h + w)
+    x, wt, b = _rand((n, h, w, 3), g), _rand((64, 3, 7, 7), g, 0.1), torch.randn(64, generator=g)
+    y = engine.stem_conv(x.to(DEV), engine.pack_stem_weight(wt.float()).to(DEV), b.to(DEV), 64, relu=True)
+    _close16(y, _ref_conv(x, wt, b, 7, relu=True, stride=2, pad=3))
