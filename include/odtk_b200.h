@@ -123,9 +123,9 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
  * odtk/backbones/fpn.py:45-61; torchvision resnet blocks): the reference has no
  * convolution kernel of its own (cuDNN through PyTorch).  Activations are NHWC fp16,
  * weights [Cout, ksize*ksize*Cin] fp16 (tap-major, channel-minor), fp32 accumulation.
- * odtk_conv2d handles stride-1 1x1 and 3x3 (pad 1) convolutions with Cin % 64 == 0 on
- * the tensor cores; strided / 7x7 convolutions are first lowered to GEMM rows with
- * odtk_lower_conv and then run as a 1x1 convolution over the lowered matrix.        */
+ * odtk_conv2d handles 1x1 and 3x3 (pad ksize/2) convolutions with Cin % 64 == 0 on the
+ * tensor cores, stride 1 or (even sizes) stride 2; odd-sized strided convolutions are first
+ * lowered to GEMM rows with odtk_lower_conv and run as a 1x1 convolution over that matrix. */
 #define ODTK_OUT_NHWC_F16 0          /* y: [N, H, W, ldy] fp16                          */
 #define ODTK_OUT_NCHW_F32 1          /* y: [N, Cout, H, W] fp32 (box head output)       */
 #define ODTK_OUT_NCHW_F32_SIGMOID 2  /* same, sigmoid applied (odtk/model.py:140)       */
@@ -137,6 +137,7 @@ typedef struct {
   const void *upsample; /* NHWC fp16 [n, h/2, width/2, cout] nearest-upsampled and added */
   void *y;
   int n, h, width, cin, cout, ksize, relu, out_mode, ldy, ldr;
+  int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2) on even h, width; y is [n, h/2, width/2, ...] */
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
 

@@ -200,6 +200,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
             const int kelems = p.row_bytes >> 1;   // K elements per block: 64 (SW128) or 32 (SW64)
             if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
+            else if (p.mode == 3) {
+              // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
+              const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
+              tma_load_5d(sa, &tmA, &bars->full[stage], pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph,
+                          h0 + (dy < 0 ? -1 : 0), img);
+            }
             else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
             else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
             tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
@@ -268,6 +274,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       dh8[k] = (p.mode != 0) ? rr / p.TW : 0;
       dw8[k] = (p.mode != 0) ? rr - dh8[k] * p.TW : rr;
     }
+    float breg[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    int bias_tile = -1;
+    static_assert(kEpiWarps == 8 || kEpiWarps == 16, "bias registers assume <= 2 segments per warp");
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
@@ -317,9 +326,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         };
+        if (p.bias && n_tile != bias_tile) {   // (re)load this warp's bias values: only when the N tile changes
+          bias_tile = n_tile;
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int cb = n0 + (sg + i * (kEpiWarps / 4)) * cpw * 16;
+            breg[i][0] = (lane < cpw * 16 && cb + lane < p.Cout) ? __ldg(p.bias + cb + lane) : 0.0f;
+            breg[i][1] = (32 + lane < cpw * 16 && cb + 32 + lane < p.Cout) ? __ldg(p.bias + cb + 32 + lane) : 0.0f;
+          }
+        }
         uint4 pre[8];
         if (has_addend) fetch(sg, pre);
-        for (int seg = sg; seg < nsegs; seg += kEpiWarps / 4) {
+        int si = 0;
+        for (int seg = sg; seg < nsegs; seg += kEpiWarps / 4, si++) {
           const int segc = min(cpw, nchunks - seg * cpw);      // 16-column chunks in this segment
           const int colbase = n0 + seg * cpw * 16;
           const bool lane_on = lx * 8 < segc * 16 && colbase + lx * 8 < p.Cout;
@@ -342,13 +361,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float f[16];
 #pragma unroll
               for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[cc & 1][j]);
-              if (p.bias && col0 < p.Cout) {
-                const float4 *bp = reinterpret_cast<const float4 *>(p.bias + col0);
+              if (p.bias) {   // lane l of the warp holds the bias of segment columns l and 32 + l
+                const float bsrc = (cc & 2) ? (si ? breg[1][1] : breg[0][1]) : (si ? breg[1][0] : breg[0][0]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                  float4 b4 = __ldg(bp + j);
-                  f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-                }
+                for (int j = 0; j < 16; j++) f[j] += __shfl_sync(0xffffffffu, bsrc, (cc & 1) * 16 + j);
               }
               unsigned char *srow = slab + lane * kSlabRowBytes;
               const int u0 = ((2 * cc) ^ (lane & 7)) << 4, u1 = u0 ^ 16;
@@ -543,7 +559,28 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     uint32_t box[2] = {64, (uint32_t)BN};
     if (!encode_map(&tmB, d->w, 2, dims, str, box)) return ODTK_E_CUDA;
   }
-  if (d->ksize == 1) {
+  const int stride = d->stride > 1 ? d->stride : 1;
+  if (stride != 1 && stride != 2) return ODTK_E_UNSUPPORTED;
+  if (stride == 2) {
+    // stride-2 1x1 / 3x3 (pad ksize/2) on even-sized inputs: 5-D parity-split view of the NHWC tensor
+    // {2C (column parity x channel), W/2, 2 (row parity), H/2, N}; out-of-range half-rows/columns
+    // (the -1 of the top/left taps) are zero-filled by the TMA unit == padding.
+    if ((d->h & 1) || (d->width & 1) || d->upsample) return ODTK_E_UNSUPPORTED;
+    const int OH = d->h / 2, OW = d->width / 2;
+    p.mode = 3;
+    p.H = OH; p.W = OW;
+    p.M = (long long)d->n * OH * OW;
+    p.up_h = OH / 2; p.up_w = OW / 2;
+    choose_patch(OH, OW, p.TH, p.TW);
+    p.tiles_h = (OH + p.TH - 1) / p.TH;
+    p.tiles_w = (OW + p.TW - 1) / p.TW;
+    p.num_m_tiles = d->n * p.tiles_h * p.tiles_w;
+    const uint64_t C = (uint64_t)d->cin, W = (uint64_t)d->width, H = (uint64_t)d->h;
+    uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (uint64_t)d->n};
+    uint64_t str[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, 1};
+    if (!encode_map(&tmA, d->x, 5, dims, str, box)) return ODTK_E_CUDA;
+  } else if (d->ksize == 1) {
     p.mode = 0;
     p.num_m_tiles = (int)((p.M + 127) / 128);
     uint64_t dims[2] = {(uint64_t)d->cin, (uint64_t)p.M};

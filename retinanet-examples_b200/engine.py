@@ -19,7 +19,7 @@ class ConvDesc(ctypes.Structure):
                 ("residual", ctypes.c_void_p), ("upsample", ctypes.c_void_p), ("y", ctypes.c_void_p),
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
                 ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
-                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int)]
+                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int)]
 
 
 def _stream():
@@ -43,23 +43,25 @@ def pack_weight(weight, kpad=None):
     return w.to(torch.float16).contiguous()
 
 
-def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None):
+def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None,
+           stride=1):
     """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
     Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
     assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
     n, h, wd, cin = x.shape
+    oh, ow = (h // 2, wd // 2) if stride == 2 else (h, wd)
     if out is None:
         if out_mode == OUT_NHWC_F16:
-            out = torch.empty((n, h, wd, cout), dtype=torch.float16, device=x.device)
+            out = torch.empty((n, oh, ow, cout), dtype=torch.float16, device=x.device)
         else:
-            out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+            out = torch.empty((n, cout, oh, ow), dtype=torch.float32, device=x.device)
     d = ConvDesc()
     d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), out.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.upsample = upsample.data_ptr() if upsample is not None else None
     d.n, d.h, d.width, d.cin, d.cout, d.ksize = n, h, wd, cin, cout, ksize
-    d.relu, d.out_mode, d.ldy, d.ldr = int(relu), out_mode, 0, 0
+    d.relu, d.out_mode, d.ldy, d.ldr, d.stride = int(relu), out_mode, 0, 0, int(stride)
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
     STATS["launches"] += 1
     return out

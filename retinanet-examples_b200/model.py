@@ -109,6 +109,10 @@ class _Conv:
         if self.direct:
             assert not in_relu
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode)
+        if (self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and not in_relu and upsample is None
+                and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0):
+            # even-sized stride-2 convolution: strided TMA view, no gather pre-pass
+            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2)
         low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
         return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode)
 

@@ -117,3 +117,13 @@ def test_stem_conv_overlapping_window_tma(n, h, w):
     x, wt, b = _rand((n, h, w, 3), g), _rand((64, 3, 7, 7), g, 0.1), torch.randn(64, generator=g)
     y = engine.stem_conv(x.to(DEV), engine.pack_stem_weight(wt.float()).to(DEV), b.to(DEV), 64, relu=True)
     _close16(y, _ref_conv(x, wt, b, 7, relu=True, stride=2, pad=3))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ks", [(2, 26, 40, 64, 128, 3), (1, 50, 80, 256, 512, 1), (1, 100, 160, 128, 128, 3),
+                                              (2, 8, 6, 512, 256, 3), (1, 200, 320, 256, 512, 1)])
+def test_strided_conv_direct_tma(n, h, w, cin, cout, ks):
+    """stride-2 1x1 / 3x3 convolutions through the parity-split 5-D tensor map (no gather)."""
+    g = torch.Generator().manual_seed(h * 7 + cin)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.03), torch.randn(cout, generator=g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, ks, relu=True, stride=2)
+    _close16(y, _ref_conv(x, wt, b, ks, relu=True, stride=2, pad=ks // 2))
