@@ -25,6 +25,7 @@
 // Strided and 7x7 convolutions are lowered by layers.cu to one of the two forms.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv.cuh"
@@ -142,18 +143,20 @@ struct Barriers {
 __device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------- kernel
+template <int CPW, bool UPS>   // CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes);
+  Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes + kEpiWarps * kSlabBytes);
   const int kStages = p.nstages, kStageBytes = kABytes + p.BN * 128;   // per-layer pipeline geometry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -253,17 +256,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int sg = (warp - 4) >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel inside the tile
-    unsigned char *slab = smem + kPipeBytes + 256 + (warp - 4) * kSlabBytes;
+    unsigned char *slab = smem + kPipeBytes + (warp - 4) * kSlabBytes;   // 1024-aligned: TMA-store source
     const int nchunks = p.BN >> 4;
     // column split: 4 segments of cpw 16-column chunks (cpw = 1, 2, 4 for BN <= 64, 128, 256);
     // a slab row holds cpw*32 bytes = lpr lanes x 16 B and one warp access covers 32/lpr rows
-    const int cpw = nchunks <= 4 ? 1 : (nchunks <= 8 ? 2 : 4);
-    const int lsh = cpw == 1 ? 1 : (cpw == 2 ? 2 : 3);
-    const int lpr = 1 << lsh, rpi = 32 >> lsh;
+    constexpr int cpw = CPW;
+    constexpr int lsh = cpw == 1 ? 1 : (cpw == 2 ? 2 : 3);
+    constexpr int lpr = 1 << lsh, rpi = 32 >> lsh;
     const int sub = lane >> lsh, lx = lane & (lpr - 1);
     const int nsegs = (nchunks + cpw - 1) / cpw;
     const bool nhwc = p.out_mode == ODTK_OUT_NHWC_F16;
-    const bool has_addend = p.residual != nullptr || p.upsample != nullptr;
+    const bool has_addend = p.residual != nullptr || (UPS && p.upsample != nullptr);
     const int hw = p.H * p.W, per_img = p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
     // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
     int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
@@ -274,6 +277,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       dh8[k] = (p.mode != 0) ? rr / p.TW : 0;
       dw8[k] = (p.mode != 0) ? rr - dh8[k] * p.TW : rr;
     }
+    int pix8[8];
+    uint4 pre[8];
+    bool prefetched = false;
     float breg[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     int bias_tile = -1;
     static_assert(kEpiWarps == 8 || kEpiWarps == 16, "bias registers assume <= 2 segments per warp");
@@ -295,9 +301,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         w0 = (r % p.tiles_w) * p.TW;
       }
       if (active && nhwc) {
-        int pix8[8];   // pixel index (-1: outside the tensor) of slab rows sub, rpi+sub, ...
+        // pix8: pixel index (-1: outside the tensor) of slab rows sub, rpi+sub, ...
 #pragma unroll
         for (int k = 0; k < 8; k++) {
+          if (prefetched) break;
           if (p.mode != 0) {
             const int rr = q * 32 + k * rpi + sub, h = h0 + dh8[k], w = w0 + dw8[k];
             pix8[k] = (k < lpr && rr < patch && h < p.H && w < p.W) ? (img0 * p.H + h) * p.W + w : -1;
@@ -306,15 +313,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             pix8[k] = (k < lpr && (long long)m < p.M) ? m : -1;
           }
         }
-        auto fetch = [&](int seg, uint4 (&dst)[8]) {
-          const int colbase = n0 + seg * cpw * 16 + lx * 8;
+        auto fetch = [&](int seg, int n0_, uint4 (&dst)[8]) {
+          const int colbase = n0_ + seg * cpw * 16 + lx * 8;
           const bool lane_on = lx * 8 < min(cpw, nchunks - seg * cpw) * 16 && colbase < p.Cout;
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             dst[k] = make_uint4(0u, 0u, 0u, 0u);
             if (pix8[k] >= 0 && lane_on) {
               if (p.residual) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
-              if (p.upsample) {
+              if (UPS && p.upsample) {
                 const int i2 = pix8[k] / hw, rem = pix8[k] - i2 * hw, h2 = rem / p.W, w2 = rem - h2 * p.W;
                 const long long up = ((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1);
                 uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.upsample + up * p.Cout + colbase));
@@ -335,19 +342,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             breg[i][1] = (32 + lane < cpw * 16 && cb + 32 + lane < p.Cout) ? __ldg(p.bias + cb + 32 + lane) : 0.0f;
           }
         }
-        uint4 pre[8];
-        if (has_addend) fetch(sg, pre);
+        if (has_addend && !prefetched) fetch(sg, n0, pre);
+        prefetched = false;
         int si = 0;
         for (int seg = sg; seg < nsegs; seg += kEpiWarps / 4, si++) {
           const int segc = min(cpw, nchunks - seg * cpw);      // 16-column chunks in this segment
           const int colbase = n0 + seg * cpw * 16;
           const bool lane_on = lx * 8 < segc * 16 && colbase + lx * 8 < p.Cout;
+          if (p.tma_store) {   // the previous bulk store must have finished READING the slab
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
           if (has_addend) {
 #pragma unroll
             for (int k = 0; k < 8; k++)
               if (k < lpr) *reinterpret_cast<uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)) = pre[k];
             __syncwarp();
-            if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, pre);
+            if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, n0, pre);
+            else if (p.tma_store && tile + (int)gridDim.x < total_tiles) {
+              // last segment of this tile: the write-out below goes through the TMA unit and no longer
+              // needs pix8, so fetch the addend of the NEXT tile's first segment now -- its DRAM latency
+              // then overlaps this segment's maths and the wait for the next accumulator
+              const int nt = tile + (int)gridDim.x, m2 = nt % p.num_m_tiles, n2 = nt / p.num_m_tiles;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                const int m = m2 * 128 + dw8[k];
+                pix8[k] = (k < lpr && (long long)m < p.M) ? m : -1;
+              }
+              fetch(sg, n2 * p.BN, pre);
+              prefetched = true;
+            }
           }
           // ---- accumulator (+bias, +staged addend, ReLU) -> fp16 into the own slab row ----
           uint32_t v[2][16];
@@ -391,6 +415,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<uint4 *>(srow + u0) = o0;
               *reinterpret_cast<uint4 *>(srow + u1) = o1;
             }
+          }
+          if (p.tma_store) {
+            // ---- slab -> global as ONE asynchronous bulk tensor store (32 rows x 128 B, 128B-swizzled
+            // exactly like the slab; rows beyond M are clipped by the TMA unit) ----
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmC), "r"(smem_u32(slab)), "r"(colbase), "r"(m_tile * 128 + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
           }
           __syncwarp();
           // ---- slab -> global: rpi rows x (lpr x 16) contiguous bytes per warp store ----
@@ -441,6 +478,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[buf]);
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -501,6 +539,23 @@ void choose_patch(int H, int W, int &TH, int &TW) {
 
 int g_num_sms = 0;
 
+template <int CPW, bool UPS>
+bool configure_one() {
+  return cudaFuncSetAttribute(conv_gemm_kernel<CPW, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) ==
+         cudaSuccess;
+}
+bool configure_kernels() {
+  return configure_one<1, false>() && configure_one<2, false>() && configure_one<4, false>() && configure_one<4, true>();
+}
+void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+                 const ConvParams &p) {
+  const int nchunks = p.BN >> 4;
+  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+}
+
 }  // namespace
 
 extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
@@ -518,8 +573,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-      return ODTK_E_CUDA;
+    if (!configure_kernels()) return ODTK_E_CUDA;
   }
   ConvParams p;
   memset(&p, 0, sizeof p);
@@ -550,6 +604,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   p.up_h = d->h / 2; p.up_w = d->width / 2;
   if (p.out_mode == ODTK_OUT_NHWC_F16 && (p.ldy % 8)) return ODTK_E_INVALID;
   if (d->upsample && ((d->h & 1) || (d->width & 1))) return ODTK_E_INVALID;
+  if (d->upsample && BN <= 128) return ODTK_E_UNSUPPORTED;  // the upsample-add epilogue is built for 256-wide tiles
 
   CUtensorMap tmA, tmB;
   const uint64_t K = (uint64_t)p.taps * d->cin;
@@ -598,11 +653,21 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
   }
+  // wide 1x1 outputs (the memory-bound layers): the epilogue hands its staged slabs to the TMA unit
+  CUtensorMap tmC = tmB;
+  static int tma_store_on = -1;
+  if (tma_store_on < 0) { const char *e = getenv("ODTK_CONV_TMA_STORE"); tma_store_on = e ? atoi(e) : 1; }
+  if (tma_store_on && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN > 128 && d->cout % 64 == 0) {
+    uint64_t dims[2] = {(uint64_t)p.ldy, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)p.ldy * 2};
+    uint32_t box[2] = {64, 32};
+    if (encode_map(&tmC, d->y, 2, dims, str, box)) p.tma_store = 1;
+  }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    conv_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+    launch_conv(grid, stream, tmA, tmB, tmC, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
@@ -623,8 +688,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-      return ODTK_E_CUDA;
+    if (!configure_kernels()) return ODTK_E_CUDA;
   }
   const int OH = h / 2, OW = width / 2, HP = h + 6, WP = width + 8;
   if ((long long)n * OH * OW >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
@@ -661,7 +725,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    conv_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+    launch_conv(grid, stream, tmA, tmB, tmB, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
