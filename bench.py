@@ -199,7 +199,10 @@ class FullWorkload:
         peak = peaks["tensor_sustained"] or peaks["tensor"]
         return {"kernel": "conv_gemm_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum summed over the 111 conv launches of ONE step
+                # (profiles/r01_conv_step_dram.csv, ncu capture of this command at ResNet50FPN batch 32)
+                "traffic": 45850652672 if (self.backbone == "ResNet50FPN" and self.batch == 32 and not self.rotated) else None,
+                "traffic_note": "bytes per step (all conv launches), from profiles/r01_conv_step_dram_summary.json",
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "avg_launch_ms": round(ms / n, 5), "launches_timed": n,
                 "algorithmic_flops_per_step": int(self.flops_per_step),
@@ -305,7 +308,8 @@ class PostprocWorkload:
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         return {"kernel": "score_filter_kernel", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peaks["hbm"], "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
-                "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                # ncu --set full capture of this kernel at batch 8 (profiles/r01_score_filter_ncu_summary.json)
+                "traffic": 497508352 if (self.batch == 8 and not self.rotated) else None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "avg_launch_ms": round(avg_ms, 5), "launches_timed": n,
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "note": "one launch per step streams the scores of all 5 levels of the batch"}
