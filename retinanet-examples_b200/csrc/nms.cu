@@ -169,7 +169,10 @@ struct NmsParams {
 };
 
 constexpr int kPosBits = 13;  // count <= 6144 < 2^13
-typedef cub::BlockRadixSort<unsigned long long, kThreads, kMaxRanks> BlockSort;
+#ifndef ODTK_NMS_RADIX_BITS
+#define ODTK_NMS_RADIX_BITS 4
+#endif
+typedef cub::BlockRadixSort<unsigned long long, kThreads, kMaxRanks, cub::NullType, ODTK_NMS_RADIX_BITS> BlockSort;
 
 // Shared memory: the radix-sort scratch is dead once the ranks sit in registers, so the
 // per-window and keeper arrays alias it.

@@ -89,3 +89,16 @@ def test_forward_end_to_end_vs_fp32_oracle():
         same = (oc[:n] == cl[i]) & (np.abs(ob[:n] - boxes[i]).max(axis=1) < 2.0) & (np.abs(os_[:n] - scores[i]) < 0.02)
         matched += bool(same.any())
     assert matched / n > 0.9, matched / n
+
+
+def test_cuda_graph_replay_equals_eager():
+    backbone, classes = "ResNet18FPN", 6
+    sd = _spread_head(make_state_dict(backbone, classes, 9, False, 12))
+    m = Model(backbone, classes=classes).load_state_dict(sd).cuda()
+    xs = [torch.randn((2, 3, 128, 256), generator=torch.Generator().manual_seed(s)).to(DEV) for s in (1, 2)]
+    eager = [[t.clone() for t in m(x)] for x in xs]
+    m.enable_cuda_graph()
+    for x, e in zip(xs + xs[:1], eager + eager[:1]):          # capture on first call, replay after
+        out = m(x)
+        for a, b in zip(out, e):
+            assert torch.equal(a, b)
