@@ -151,7 +151,11 @@ class FullWorkload:
     def step_profile(self):
         """Same step launched eagerly (a CUDA-graph replay runs no host code, so the per-kernel
         CUDA events of the roofline pass can only be recorded around eager launches)."""
-        self.out = self._gather(self.model.forward(self.dev_x))
+        self.model.parallel_heads = False       # one stream: per-kernel event times must not overlap
+        try:
+            self.out = self._gather(self.model.forward(self.dev_x))
+        finally:
+            self.model.parallel_heads = True
 
     def step_e2e(self):
         """One end-to-end step through the public API: this step's images travel pinned host -> device,

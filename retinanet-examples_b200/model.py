@@ -147,6 +147,8 @@ class Model:
         self._sd = None
         self._packed = None
         self.device = None
+        self.parallel_heads = True
+        self._head_streams = None
 
     def __repr__(self):
         return '\n'.join(['     model: {}'.format(self.name), '  backbone: {}'.format(self.backbone),
@@ -252,17 +254,46 @@ class Model:
         return [P["smooth3"](p3), P["smooth4"](p4), P["smooth5"](p5), p6, p7]
 
     def _heads(self, features, sigmoid=True):
+        """Class / box heads on the five levels (odtk/model.py:134-135).  The ten conv chains are
+        independent, so each runs on its own CUDA stream (fork after the FPN, join before decode): the
+        small levels' launches (P5-P7 use 1-32 CTAs) overlap each other and the tail of the big
+        ones; inside a CUDA graph the chains become parallel branches."""
         P = self._packed
-        cls_heads, box_heads = [], []
-        for t in features:
-            c = t
-            for conv in P["cls_head"][:-1]:
-                c = conv(c, relu=True)
-            cls_heads.append(P["cls_head"][-1](c, out_mode=engine.OUT_NCHW_F32_SIGMOID if sigmoid else engine.OUT_NCHW_F32))
-            b = t
-            for conv in P["box_head"][:-1]:
-                b = conv(b, relu=True)
-            box_heads.append(P["box_head"][-1](b, out_mode=engine.OUT_NCHW_F32))
+        nl = len(features)
+        cls_heads, box_heads = [None] * nl, [None] * nl
+        cls_mode = engine.OUT_NCHW_F32_SIGMOID if sigmoid else engine.OUT_NCHW_F32
+
+        def chain(head, t, final_mode):
+            for conv in P[head][:-1]:
+                t = conv(t, relu=True)
+            return P[head][-1](t, out_mode=final_mode)
+
+        if not self.parallel_heads:
+            for i, t in enumerate(features):
+                cls_heads[i] = chain("cls_head", t, cls_mode)
+                box_heads[i] = chain("box_head", t, engine.OUT_NCHW_F32)
+            return cls_heads, box_heads
+        main = torch.cuda.current_stream()
+        if self._head_streams is None or len(self._head_streams) < 2 * nl:
+            self._head_streams = [torch.cuda.Stream(device=self.device) for _ in range(2 * nl)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for i, t in enumerate(features):
+            for j, (head, mode) in enumerate((("cls_head", cls_mode), ("box_head", engine.OUT_NCHW_F32))):
+                if i == 0 and j == 0:          # the biggest chain stays on the main stream
+                    cls_heads[0] = chain(head, t, mode)
+                    continue
+                st = self._head_streams[2 * i + j]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    out = chain(head, t, mode)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                joins.append(ev)
+                (cls_heads if j == 0 else box_heads)[i] = out
+        for ev in joins:
+            main.wait_event(ev)
         return cls_heads, box_heads
 
     @staticmethod

@@ -102,3 +102,18 @@ def test_cuda_graph_replay_equals_eager():
         out = m(x)
         for a, b in zip(out, e):
             assert torch.equal(a, b)
+
+
+def test_parallel_head_streams_equal_sequential():
+    backbone, classes = "ResNet18FPN", 6
+    sd = _spread_head(make_state_dict(backbone, classes, 9, False, 13))
+    m = Model(backbone, classes=classes).load_state_dict(sd).cuda()
+    x = torch.randn((2, 3, 256, 256), generator=torch.Generator().manual_seed(3)).to(DEV)
+    m.parallel_heads = False
+    seq = [t.clone() for t in m(x)]
+    m.parallel_heads = True
+    for _ in range(3):
+        par = m(x)
+        torch.cuda.synchronize()
+        for a, b in zip(par, seq):
+            assert torch.equal(a, b)
