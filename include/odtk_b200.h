@@ -170,6 +170,20 @@ long long odtk_focal_loss(const float *logits, const float *target, const float 
                           float *loss_elem, float *loss_sum, float *grad, void *workspace,
                           size_t workspace_size, odtk_stream_t stream);
 
+/* Smooth L1 (odtk/loss.py:27-31; box loss of Model._compute_loss, odtk/model.py:201-205), same fused
+ * forward + backward + masked-sum form as odtk_focal_loss.  SURVEY.md section 8f, row 1.            */
+long long odtk_smooth_l1_loss(const float *pred, const float *target, const float *mask, long long n,
+                              float beta, float grad_scale, float *loss_elem, float *loss_sum, float *grad,
+                              void *workspace, size_t workspace_size, odtk_stream_t stream);
+
+/* ---- input side of `odtk infer` ---------------------------------------
+ * Replaces the per-image tensor maths of CocoDataset.__getitem__ (odtk/data.py:113-123): uint8 HWC
+ * [n,h,w,3] -> /255 -> (x - mean)/std -> zero padding to [hs, ws] (a multiple of the model stride),
+ * written straight into the zero-padded NHWC4 fp16 buffer [n, hs+6, ws+8, 4] that odtk_stem_conv
+ * reads (no fp32 image, no separate pad).  mean / std: 3 host floats.                                 */
+int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, int hs, int ws, const float *mean,
+                       const float *std, odtk_stream_t stream);
+
 /* ---- per-kernel timing (B200-native addition; the reference has only a wall-clock
  * Profiler without CUDA sync, odtk/utils.py:140-167) ------------------------------
  * When enabled, every launch of a tagged kernel is bracketed by CUDA events on the

@@ -134,5 +134,28 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def gen_l1_preproc(odtk):
+    """SmoothL1Loss + autograd (odtk/loss.py:27-31) and the tensor maths of CocoDataset.__getitem__
+    (odtk/data.py:113-123: float().div(255), per-channel sub_(mean).div_(std), F.pad to the stride) run
+    verbatim on seeded inputs (the dataset class itself needs pycocotools + image files)."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    p = rng.normal(0, 0.3, size=(2, 36, 5, 7)).astype(np.float32)
+    t = rng.normal(0, 0.3, size=p.shape).astype(np.float32)
+    pt = torch.from_numpy(p).requires_grad_(True)
+    loss = odtk.loss.SmoothL1Loss(beta=0.11)(pt, torch.from_numpy(t))
+    loss.sum().backward()
+    img = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    data = torch.from_numpy(img.copy()).float().div(255).permute(2, 0, 1).contiguous()
+    for tt, mean, std in zip(data, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]):
+        tt.sub_(mean).div_(std)
+    pw, ph = ((128 - d % 128) % 128 for d in (53, 37))
+    data = F.pad(data, (0, pw, 0, ph))
+    np.savez_compressed(os.path.join(OUT, "l1_preproc.npz"), p=p, t=t, loss=loss.detach().numpy(),
+                        grad=pt.grad.numpy(), img=img, pre=data.numpy())
+
+
 if __name__ == "__main__":
     main()
+    if len(sys.argv) == 1 or "l1" in sys.argv[1:]:
+        gen_l1_preproc(ref_import.import_reference())

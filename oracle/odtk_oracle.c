@@ -362,3 +362,32 @@ double oracle_focal_loss(const float *logits, const float *target, const float *
   }
   return total;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Smooth L1 forward + analytic backward: odtk/loss.py:27-31.                  */
+double oracle_smooth_l1(const float *pred, const float *target, const float *mask, int64_t n, float beta,
+                        float grad_scale, float *loss_out, float *grad_out) {
+  double total = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    double d = (double)pred[i] - (double)target[i], x = fabs(d), m = mask ? mask[i] : 1.0;
+    double l = (x >= beta) ? x - 0.5 * beta : 0.5 * x * x / beta;
+    if (loss_out) loss_out[i] = (float)(m * l);
+    total += m * l;
+    if (grad_out) grad_out[i] = (float)(m * grad_scale * ((x >= beta) ? (d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0)) : d / beta));
+  }
+  return total;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Input normalisation + stride padding: odtk/data.py:113-123 (float32 maths). */
+/* x: uint8 [h, w, 3]; out: float32 [3, hs, ws] (CHW like the reference).      */
+void oracle_preprocess_u8(const uint8_t *x, int h, int w, int hs, int ws, const float *mean, const float *std,
+                          float *out) {
+  for (int c = 0; c < 3; c++)
+    for (int y = 0; y < hs; y++)
+      for (int xx = 0; xx < ws; xx++) {
+        float v = 0.0f;
+        if (y < h && xx < w) v = ((float)x[((size_t)y * w + xx) * 3 + c] / 255.0f - mean[c]) / std[c];
+        out[((size_t)c * hs + y) * ws + xx] = v;
+      }
+}

@@ -42,6 +42,10 @@ def lib():
         L.oracle_focal_loss.restype = ctypes.c_double
         L.oracle_focal_loss.argtypes = [f32p, f32p, f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, f32p, f32p]
+        L.oracle_smooth_l1.restype = ctypes.c_double
+        L.oracle_smooth_l1.argtypes = [f32p, f32p, f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_float, f32p, f32p]
+        L.oracle_preprocess_u8.restype = None
+        L.oracle_preprocess_u8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p, f32p, f32p]
         _LIB = L
     return _LIB
 
@@ -141,3 +145,22 @@ def generate_anchors_rotated_axis(stride, ratio_vals, scales_vals, angles_vals):
 DEFAULT_RATIOS = [1.0, 2.0, 0.5]
 DEFAULT_SCALES = [4 * 2 ** (i / 3) for i in range(3)]
 DEFAULT_ANGLES = [-math.pi / 6, 0, math.pi / 6]
+
+
+def smooth_l1(pred, target, mask=None, beta=0.11, grad_scale=1.0):
+    """odtk/loss.py:27-31.  Returns (masked sum, per-element loss, grad of the sum * grad_scale)."""
+    x, t = _f32(pred).reshape(-1), _f32(target).reshape(-1)
+    m = None if mask is None else _f32(mask).reshape(-1)
+    lo, g = np.empty_like(x), np.empty_like(x)
+    tot = lib().oracle_smooth_l1(_p(x), _p(t), _p(m) if m is not None else None, x.size, beta, grad_scale, _p(lo), _p(g))
+    return tot, lo, g
+
+
+def preprocess_u8(image, stride=128, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """odtk/data.py:113-123: uint8 [H, W, 3] -> float32 [3, Hs, Ws] normalised and zero-padded."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    h, w, _ = img.shape
+    hs, ws = (h + stride - 1) // stride * stride, (w + stride - 1) // stride * stride
+    out = np.empty((3, hs, ws), np.float32)
+    lib().oracle_preprocess_u8(img.ctypes.data_as(ctypes.c_void_p), h, w, hs, ws, _p(_f32(mean)), _p(_f32(std)), _p(out))
+    return out

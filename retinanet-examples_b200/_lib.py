@@ -46,6 +46,9 @@ SIGNATURES = {
     "odtk_focal_loss": (ctypes.c_longlong, [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, ctypes.c_float, ctypes.c_float] + [ctypes.c_void_p] * 4 +
                         [ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_smooth_l1_loss": (ctypes.c_longlong, [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_float, ctypes.c_float] +
+                            [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_preprocess_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [_c_f32p, _c_f32p, ctypes.c_void_p]),
     "odtk_prof_enable": (None, [ctypes.c_int]),
     "odtk_prof_reset": (None, []),
     "odtk_prof_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),

@@ -123,6 +123,33 @@ __global__ void pad_input_kernel(const __half *__restrict__ x, __half *__restric
   }
 }
 
+// Input side of odtk infer (reference odtk/data.py:113-123): uint8 HWC image -> /255 -> (x - mean) / std
+// -> zero padding to a multiple of the model stride, fused with the stem's own zero padding and the
+// RGB -> NHWC4 widening: one 8-byte store per padded pixel, the fp32 full-image pass disappears.
+__global__ void preprocess_u8_kernel(const unsigned char *__restrict__ x, __half *__restrict__ y, int N, int H, int W,
+                                     int HS, int WS, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int HP = HS + 6, WP = WS + 8;
+  const long long total = (long long)N * HP * WP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int xp = (int)(i % WP);
+    long long t = i / WP;
+    int yp = (int)(t % HP);
+    int n = (int)(t / HP);
+    int ih = yp - 3, iw = xp - 3;
+    uint2 v = make_uint2(0u, 0u);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const unsigned char *s = x + (((long long)n * H + ih) * W + iw) * 3;
+      // same operation order as the reference: float(u8) / 255, then - mean, then / std
+      float r = ((float)s[0] / 255.0f - m0) / s0, g = ((float)s[1] / 255.0f - m1) / s1, b = ((float)s[2] / 255.0f - m2) / s2;
+      __half2 rg = __floats2half2_rn(r, g);
+      __half2 bz = __floats2half2_rn(b, 0.0f);
+      v.x = *reinterpret_cast<unsigned *>(&rg);
+      v.y = *reinterpret_cast<unsigned *>(&bz);
+    }
+    reinterpret_cast<uint2 *>(y)[i] = v;
+  }
+}
+
 inline int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = 148ll * 16;
@@ -164,5 +191,14 @@ extern "C" int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_
   if (!x || !y || n <= 0 || h <= 0 || w <= 0) return ODTK_E_INVALID;
   long long total = (long long)n * (h + 6) * (w + 8);
   pad_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, int hs, int ws, const float *mean,
+                                  const float *std, odtk_stream_t stream_) {
+  if (!x || !y || !mean || !std || n <= 0 || h <= 0 || w <= 0 || hs < h || ws < w) return ODTK_E_INVALID;
+  long long total = (long long)n * (hs + 6) * (ws + 8);
+  preprocess_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+      (const unsigned char *)x, (__half *)y, n, h, w, hs, ws, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -114,6 +114,32 @@ __global__ void __launch_bounds__(kThreads) focal_loss_kernel(LossParams p) {
   }
 }
 
+// Smooth L1 (reference odtk/loss.py:27-31): x = |pred - target|; x >= beta ? x - beta/2 : x^2 / (2 beta);
+// masked sum + gradient in the same pass (box regression loss of Model._compute_loss, model.py:201-205).
+__global__ void __launch_bounds__(kThreads) smooth_l1_kernel(const float *pred, const float *target, const float *mask,
+                                                             long long n, float beta, float grad_scale,
+                                                             float *loss_elem, float *grad, double *partials) {
+  __shared__ double s_part[kThreads / 32];
+  double acc = 0.0;
+  for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < n; e += (long long)gridDim.x * kThreads) {
+    const float d = pred[e] - target[e], x = fabsf(d), m = mask ? mask[e] : 1.0f;
+    const bool lin = x >= beta;
+    const float l = m * (lin ? x - 0.5f * beta : 0.5f * x * x / beta);
+    acc += (double)l;
+    if (loss_elem) loss_elem[e] = l;
+    if (grad) grad[e] = m * grad_scale * (lin ? (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) : d / beta);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; w++) s += s_part[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
 __global__ void focal_loss_finish_kernel(const double *partials, int n, float *out) {
   double s = 0.0;
   for (int i = 0; i < n; i++) s += partials[i];  // fixed order: deterministic
@@ -154,5 +180,24 @@ extern "C" long long odtk_focal_loss(const float *logits, const float *target, c
     focal_loss_kernel<<<grid, kThreads, 0, stream>>>(p);
   }
   focal_loss_finish_kernel<<<1, 1, 0, stream>>>(p.partials, grid, loss_sum);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" long long odtk_smooth_l1_loss(const float *pred, const float *target, const float *mask, long long n,
+                                         float beta, float grad_scale, float *loss_elem, float *loss_sum, float *grad,
+                                         void *workspace, size_t workspace_size, odtk_stream_t stream_) {
+  if (n <= 0 || !(beta > 0.0f)) return ODTK_E_INVALID;
+  const int grid = loss_grid(n);
+  const size_t need = odtk_align_up((size_t)grid * sizeof(double));
+  if (!workspace || !workspace_size) return (long long)need;
+  if (workspace_size < need) return ODTK_E_WORKSPACE;
+  if (!pred || !target || !loss_sum) return ODTK_E_INVALID;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  {
+    OdtkProfScope prof(ODTK_PROF_LOSS, stream);
+    smooth_l1_kernel<<<grid, kThreads, 0, stream>>>(pred, target, mask, n, beta, grad_scale, loss_elem, grad,
+                                                    (double *)workspace);
+  }
+  focal_loss_finish_kernel<<<1, 1, 0, stream>>>((const double *)workspace, grid, loss_sum);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

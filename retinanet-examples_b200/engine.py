@@ -97,6 +97,35 @@ def pack_stem_weight(weight):
     return w.reshape(cout, 224).to(torch.float16).contiguous()
 
 
+IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]   # odtk/data.py:25-26
+
+
+def preprocess_u8(images, stride=128, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 HWC batch [N,H,W,3] (CUDA) -> normalised, stride-padded, zero-bordered NHWC4 fp16
+    [N, Hs+6, Ws+8, 4] ready for the stem (reference: odtk/data.py:113-123).  Returns (buffer, Hs, Ws)."""
+    assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.shape[-1] == 3
+    n, h, w, _ = images.shape
+    hs, ws = (h + stride - 1) // stride * stride, (w + stride - 1) // stride * stride
+    xp = torch.empty((n, hs + 6, ws + 8, 4), dtype=torch.float16, device=images.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    _lib.check(_lib.lib().odtk_preprocess_u8(ctypes.c_void_p(images.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, w,
+                                             hs, ws, m, s, _stream()), "preprocess_u8")
+    STATS["launches"] += 1
+    return xp, hs, ws
+
+
+def stem_conv_padded(xp, h, wd, w, bias, cout, relu=True):
+    """Stem over an already padded NHWC4 buffer [N, h+6, wd+8, 4] (from preprocess_u8)."""
+    n = xp.shape[0]
+    out = torch.empty((n, h // 2, wd // 2, cout), dtype=torch.float16, device=xp.device)
+    _lib.check(_lib.lib().odtk_stem_conv(ctypes.c_void_p(xp.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+                                         ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                         ctypes.c_void_p(out.data_ptr()), n, h, wd, cout, int(relu), _stream()), "stem_conv")
+    STATS["launches"] += 1
+    return out
+
+
 def stem_conv(x, w, bias, cout, relu=True):
     """7x7 stride-2 pad-3 convolution of an NHWC fp16 RGB batch [N,H,W,3] on the tensor cores:
     zero-pad to NHWC4 (one small kernel), then the conv kernel in stem mode.  Returns

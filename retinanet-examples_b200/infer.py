@@ -52,3 +52,22 @@ def infer(model, path, detections_file=None, resize=None, max_size=None, batch_s
             results.append(pack_detections(scores, boxes, classes))
     packed = torch.cat(results, dim=0)
     return gather_detections(*unpack_detections(packed), world=max(world, 1))
+
+
+def detections_to_coco(scores, boxes, classes, ratios, image_ids=None, category_ids=None):
+    """Output side of `odtk infer` (odtk/infer.py:104-148, axis-aligned branch): keep score > 0, undo the
+    resize ratio, convert (x1, y1, x2, y2) to COCO (x, y, w, h) with the +1 width convention.
+    scores [N, D], boxes [N, D, 4], classes [N, D]; ratios [N] or scalar.  Returns a list of dicts."""
+    scores, boxes, classes = scores.float().cpu(), boxes.float().cpu(), classes.float().cpu()
+    ratios = torch.as_tensor(ratios, dtype=torch.float32).reshape(-1).expand(scores.shape[0]) if not torch.is_tensor(ratios) \
+        else ratios.float().cpu().reshape(-1).expand(scores.shape[0])
+    out = []
+    for i in range(scores.shape[0]):
+        keep = (scores[i] > 0).nonzero(as_tuple=False).view(-1)
+        b = boxes[i][keep] / ratios[i]
+        for score, box, cat in zip(scores[i][keep].tolist(), b.tolist(), classes[i][keep].int().tolist()):
+            x1, y1, x2, y2 = box
+            out.append({"image_id": int(image_ids[i]) if image_ids is not None else i, "score": score,
+                        "category_id": category_ids[cat] if category_ids is not None else cat,
+                        "bbox": [x1, y1, x2 - x1 + 1, y2 - y1 + 1]})
+    return out

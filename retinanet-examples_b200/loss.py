@@ -68,3 +68,55 @@ def focal_loss_sum(pred_logits, target=None, mask=None, cls_index=None, alpha=0.
     t = target.float().contiguous()
     m = mask.float().expand_as(t).contiguous() if mask is not None else None
     return _FocalSum.apply(pred_logits, t, m, None, 0, 0, alpha, gamma)
+
+
+class SmoothL1Loss:
+    'Smooth L1 Loss (reference: odtk/loss.py:20-31)'
+
+    def __init__(self, beta=0.11):
+        self.beta = beta
+
+    def forward(self, pred, target):
+        _, elem, _ = _launch_l1(pred, target, None, self.beta, 1.0, True, False)
+        return elem.view_as(pred)
+
+    __call__ = forward
+
+
+def _launch_l1(pred, target, mask, beta, grad_scale, want_elem, want_grad):
+    if not pred.is_cuda:
+        raise RuntimeError("pred must be a CUDA tensor")
+    L = _lib.lib()
+    x, t = pred.float().contiguous(), target.float().contiguous()
+    m = mask.float().expand_as(x).contiguous() if mask is not None else None
+    elem = torch.empty_like(x) if want_elem else None
+    grad = torch.empty_like(x) if want_grad else None
+    total = torch.empty(1, dtype=torch.float32, device=x.device)
+
+    def p(v):
+        return ctypes.c_void_p(v.data_ptr()) if v is not None else None
+    args = (p(x), p(t), p(m), x.numel(), float(beta), float(grad_scale), p(elem), p(total), p(grad))
+    size = _lib.check(L.odtk_smooth_l1_loss(*args, None, 0, None), "smooth_l1 (workspace query)")
+    ws = torch.empty(int(size), dtype=torch.uint8, device=x.device)
+    _lib.check(L.odtk_smooth_l1_loss(*args, ctypes.c_void_p(ws.data_ptr()), size,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "smooth_l1")
+    return total, elem, grad
+
+
+class _L1Sum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, beta):
+        total, _, grad = _launch_l1(pred, target, mask, beta, 1.0, False, True)
+        ctx.save_for_backward(grad.view_as(pred))
+        return total[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def smooth_l1_loss_sum(pred, target, mask=None, beta=0.11):
+    """sum(mask * SmoothL1Loss(pred, target)) with its gradient in the same pass
+    (== `(box_mask * box_criterion(box_head, box_target)).sum()`, odtk/model.py:201-205)."""
+    return _L1Sum.apply(pred, target, mask, beta)

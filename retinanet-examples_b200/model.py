@@ -230,9 +230,10 @@ class Model:
         self._packed = P
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _features(self, x):
+    def _features(self, x, stem_done=False):
         P = self._packed
-        x = P["stem"](x, relu=True)
+        if not stem_done:
+            x = P["stem"](x, relu=True)
         x = engine.maxpool3x3s2(x)
         outs = {}
         for blk in P["blocks"]:
@@ -302,6 +303,19 @@ class Model:
             raise ValueError("expected a [B, 3, H, W] batch")
         return x.permute(0, 2, 3, 1).contiguous().to(torch.float16)   # zero-copy for channels_last fp16
 
+    def forward_heads_u8(self, images, sigmoid=True):
+        """Input side of `odtk infer` fused in: `images` is a uint8 HWC batch
+        [B, H, W, 3]; normalisation, stride padding (odtk/data.py:113-123) and the stem's zero border are one
+        kernel that writes the stem's input buffer directly."""
+        if self._packed is None:
+            raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
+        P = self._packed
+        xp, hs, ws = engine.preprocess_u8(images, self.stride)
+        stem = P["stem"]
+        engine.STATS["conv_flops"] += 2 * images.shape[0] * (hs // 2) * (ws // 2) * stem.cout * 49 * 3
+        x = engine.stem_conv_padded(xp, hs, ws, stem.w_stem, stem.b, stem.cout, relu=True)
+        return self._heads(self._features(x, stem_done=True), sigmoid), (hs, ws)
+
     def forward_heads(self, x, sigmoid=True):
         """The `exporting=True` view of the reference (odtk/model.py:142-144): per-level
         (sigmoid) class maps [B, A*C, H, W] and box maps [B, A*4|6, H, W], fp32 NCHW."""
@@ -310,13 +324,17 @@ class Model:
         return self._heads(self._features(self._to_nhwc_half(x)), sigmoid)
 
     def forward(self, x, rotated_bbox=None):
-        cls_heads, box_heads = self.forward_heads(x)
+        if x.dtype == torch.uint8:                       # raw HWC images: fused input side
+            (cls_heads, box_heads), (_, width) = self.forward_heads_u8(x)
+        else:
+            cls_heads, box_heads = self.forward_heads(x)
+            width = x.shape[-1]
         if self.exporting:
-            self.strides = [x.shape[-1] // c.shape[-1] for c in cls_heads]
+            self.strides = [width // c.shape[-1] for c in cls_heads]
             return cls_heads, box_heads
         strides, anchors = [], []
         for c in cls_heads:
-            stride = x.shape[-1] // c.shape[-1]            # width only (odtk/model.py:155)
+            stride = width // c.shape[-1]                  # width only (odtk/model.py:155)
             if stride not in self.anchors:
                 self.anchors[stride] = (box.generate_anchors_rotated(stride, self.ratios, self.scales, self.angles)
                                         if self.rotated_bbox else box.generate_anchors(stride, self.ratios, self.scales))

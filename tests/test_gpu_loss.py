@@ -58,3 +58,22 @@ def test_focal_class_index_targets_equal_dense_one_hot():
     assert torch.equal(xa.grad, xb.grad)
     tot, _, _ = oracle.focal_loss(x, t, m)
     np.testing.assert_allclose(float(lb), tot, rtol=2e-5)
+
+
+def test_smooth_l1_matches_reference_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "l1_preproc.npz"))
+    p = torch.from_numpy(g["p"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(g["t"]).to(DEV)
+    elem = loss_mod.SmoothL1Loss(beta=0.11)(p.detach(), t)
+    np.testing.assert_allclose(elem.cpu().numpy(), g["loss"], rtol=1e-5, atol=1e-7)
+    total = loss_mod.smooth_l1_loss_sum(p, t)
+    total.backward()
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad"], rtol=1e-5, atol=1e-6)
+    rng = np.random.default_rng(4)
+    m = (rng.uniform(size=g["p"].shape) < 0.5).astype(np.float32)
+    tot, _, gr = oracle.smooth_l1(g["p"], g["t"], m)
+    p2 = torch.from_numpy(g["p"]).to(DEV).requires_grad_(True)
+    l2 = loss_mod.smooth_l1_loss_sum(p2, t, torch.from_numpy(m).to(DEV))
+    l2.backward()
+    np.testing.assert_allclose(float(l2), tot, rtol=1e-5)
+    np.testing.assert_allclose(p2.grad.cpu().numpy().reshape(-1), gr, rtol=1e-5, atol=1e-6)

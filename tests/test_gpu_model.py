@@ -117,3 +117,33 @@ def test_parallel_head_streams_equal_sequential():
         torch.cuda.synchronize()
         for a, b in zip(par, seq):
             assert torch.equal(a, b)
+
+
+def test_uint8_input_side_fused(golden_dir):
+    """uint8 HWC images -> normalise + stride pad (odtk/data.py:113-123) fused into the stem's input buffer."""
+    from retinanet_examples_b200 import engine
+    from oracle import oracle
+    g = np.load(os.path.join(golden_dir, "l1_preproc.npz"))
+    img = torch.from_numpy(g["img"])[None].to(DEV)                       # [1, 37, 53, 3] uint8
+    xp, hs, ws = engine.preprocess_u8(img, 128)
+    assert (hs, ws) == (128, 128)
+    inner = xp[0, 3:3 + hs, 3:3 + ws, :3].permute(2, 0, 1).float().cpu().numpy()
+    np.testing.assert_allclose(inner, g["pre"], rtol=1e-3, atol=1e-3)        # fp16 storage of the fp32 reference values
+    assert float(xp[0, :3].abs().max()) == 0 and float(xp[0, :, :3].abs().max()) == 0 and float(xp[..., 3].abs().max()) == 0
+    # whole model from uint8 == whole model from the oracle-preprocessed float image
+    backbone, classes = "ResNet18FPN", 6
+    sd = _spread_head(make_state_dict(backbone, classes, 9, False, 14))
+    m = Model(backbone, classes=classes).load_state_dict(sd).cuda()
+    imgs = torch.randint(0, 256, (2, 100, 200, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
+    out_u8 = m(imgs.to(DEV))
+    ref_in = torch.from_numpy(np.stack([oracle.preprocess_u8(i.numpy()) for i in imgs]))
+    out_f = m(ref_in.to(DEV))
+    for a, b in zip(out_u8, out_f):
+        assert torch.equal(a, b)
+
+
+def test_detections_to_coco_output_side():
+    from retinanet_examples_b200 import infer
+    s = torch.tensor([[0.9, 0.0, 0.5]]); b = torch.tensor([[[10., 20., 30., 60.], [0, 0, 0, 0], [2., 4., 6., 8.]]]); c = torch.tensor([[3., 0., 1.]])
+    d = infer.detections_to_coco(s, b, c, ratios=2.0)
+    assert len(d) == 2 and d[0]["bbox"] == [5.0, 10.0, 11.0, 21.0] and d[0]["category_id"] == 3 and d[1]["bbox"] == [1.0, 2.0, 3.0, 3.0]

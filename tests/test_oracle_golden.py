@@ -127,3 +127,15 @@ def test_oracle_against_live_reference_nms():
         nk = int((rs[0] > 0).sum())
         np.testing.assert_array_equal(os_[0][:nk], rs[0][:nk])
         np.testing.assert_array_equal(ob[0][:nk], rb[0][:nk])
+
+
+def test_l1_and_preprocess_oracle_match_reference(golden_dir):
+    """Fixture: reference odtk.loss.SmoothL1Loss(beta=.11) + autograd on seeded inputs, and the tensor maths of
+    odtk/data.py:113-123 (float().div(255), per-channel sub_(mean).div_(std), F.pad to stride 128) run verbatim on a
+    seeded uint8 image (generated in the build container with the reference imported from /root/reference)."""
+    g = _load(golden_dir, "l1_preproc.npz")
+    tot, lo, gr = oracle.smooth_l1(g["p"], g["t"])
+    np.testing.assert_allclose(lo.reshape(g["loss"].shape), g["loss"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(gr.reshape(g["grad"].shape), g["grad"], rtol=1e-5, atol=1e-6)
+    pre = oracle.preprocess_u8(g["img"])
+    np.testing.assert_allclose(pre, g["pre"], rtol=1e-6, atol=1e-6)
