@@ -9,15 +9,13 @@
 //
 //   1. unique composite keys (score key << 13 | ~position) for scores > 0, one block-wide
 //      cub radix sort (45 bits) == the reference's stable descending device radix sort;
-//   2. the ranks are walked in windows of 1024 (one rank per thread): a window is first
-//      pruned against the keepers of earlier windows, then a greedy loop runs over its
-//      KEEPERS only (the reference loops over every candidate): each iteration broadcasts the
-//      keeper from shared memory, every thread tests its own rank (class gate first, IEEE
-//      division, +1 widths) and clears its bit in a 32-word survivor bitmap that all threads
-//      scan for the next keeper.  The walk stops at detections_per_im keepers -- exact,
-//      because the output is the first D entries of (kept..., suppressed...) and later
-//      candidates never change earlier decisions (SURVEY.md section 8 note N1); with the
-//      BASELINE workload only the first window is ever touched;
+//   2. the ranks are resolved in chunks of 128: every candidate of the chunk is tested against the
+//      keepers of earlier chunks, the same-class / overlap relation inside the chunk is evaluated
+//      for all pairs at once into a 128 x 128 bit matrix (class gate first, IEEE division, +1
+//      widths), and one warp resolves the chunk sequentially with bit operations only.  The walk
+//      stops at detections_per_im keepers -- exact, because the output is the first D entries of
+//      (kept..., suppressed...) and later candidates never change earlier decisions (SURVEY.md
+//      section 8 note N1); with the BASELINE workload one chunk is enough;
 //   3. if fewer than D were kept the tail is the first suppressed candidates in rank order
 //      with score 0 and their boxes/classes, exactly what the reference's second sort
 //      leaves there (nms.cu:146-156).
@@ -169,6 +167,7 @@ struct NmsParams {
 };
 
 constexpr int kPosBits = 13;  // count <= 6144 < 2^13
+constexpr int kChunk = 128;   // ranks resolved per round
 #ifndef ODTK_NMS_RADIX_BITS
 #define ODTK_NMS_RADIX_BITS 4
 #endif
@@ -179,8 +178,11 @@ typedef cub::BlockRadixSort<unsigned long long, kThreads, kMaxRanks, cub::NullTy
 template <int NBOX>
 struct NmsSmem {
   struct Data {
-    float wbox[kThreads][NBOX];   // current window, by window-local rank
-    int wcls[kThreads];
+    float cbox[kChunk][NBOX];     // current chunk of 128 ranks
+    int ccls[kChunk];
+    int cidx[kChunk];
+    int prevsup[kChunk];          // suppressed by a keeper of an earlier chunk
+    unsigned mask[kChunk][kChunk / 32];   // bit j of row i: j < i would suppress i if it survives
     float kbox[kMaxDet][NBOX];    // keepers so far
     int kcls[kMaxDet];
     int kidx[kMaxDet];
@@ -196,8 +198,7 @@ template <int NBOX>
 __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typename NmsSmem<NBOX>::U &sm = *reinterpret_cast<typename NmsSmem<NBOX>::U *>(smem_raw);
-  __shared__ unsigned s_alive[kThreads / 32];
-  __shared__ int s_wsum[32];
+  __shared__ int s_kept, s_ntail;
   __shared__ int s_n;
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -235,106 +236,95 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   const int n = s_n;
   const int nd = n < D ? n : D;
 
-  // ---- 2. windows of 1024 ranks: prune against the keepers so far, then greedy ---------
+  // ---- 2. greedy NMS in chunks of 128 ranks (nms_kernel, nms.cu:49-79) ---------------------
+  // Per chunk: (A) every candidate is tested against the keepers of earlier chunks, (B) the
+  // same-class / overlap relation INSIDE the chunk is evaluated for all pairs at once into a
+  // 128 x 128 bit matrix, (C) one warp resolves the chunk sequentially with bit operations only
+  // (candidate i survives iff no earlier SURVIVOR of the chunk has its bit set in row i).  All
+  // floating-point work is parallel; the serial part is ~30 cycles per candidate and stops at D
+  // keepers -- the reference's kernel runs one block-wide barrier per candidate instead.
   int kept = 0, ntail = 0;
-  const int nwin = (n + kThreads - 1) / kThreads;
+  const int nchunk = (n + kChunk - 1) / kChunk;
+  if (t == 0) { s_kept = 0; s_ntail = 0; }
+  __syncthreads();
 #pragma unroll 1
-  for (int w = 0; w < nwin && kept < D; w++) {
-    const int r = t + w * kThreads;
-    const bool valid = r < n;
-    // select keys[w] without dynamic register indexing
-    unsigned long long key = 0ull;
+  for (int c = 0; c < nchunk && kept < D; c++) {
+    const int r0 = c * kChunk, cn = min(kChunk, n - r0);
+    // the chunk's ranks live in threads (r0 + i) % 1024, register slot (r0 + i) / 1024
+    {
+      const int i = t - (r0 % kThreads);
+      if (i >= 0 && i < cn) {
+        unsigned long long key = 0ull;
+        const int slot = r0 / kThreads;
 #pragma unroll
-    for (int k = 0; k < kMaxRanks; k++)
-      if (k == w) key = keys[k];
-    const int idx = valid ? (int)((~(unsigned)key) & ((1u << kPosBits) - 1u)) : 0;
-    float ib[NBOX];
-    int icls = -1;
-    if (valid) {
-      if (NBOX == 4) {
-        float4 b = *reinterpret_cast<const float4 *>(bx + (long long)idx * 4);
-        ib[0] = b.x; ib[1] = b.y; ib[2] = b.z; ib[3] = b.w;
-      } else {
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k == slot) key = keys[k];
+        const int idx = (int)((~(unsigned)key) & ((1u << kPosBits) - 1u));
+        if (NBOX == 4) {
+          *reinterpret_cast<float4 *>(sm.d.cbox[i]) = *reinterpret_cast<const float4 *>(bx + (long long)idx * 4);
+        } else {
 #pragma unroll
-        for (int q = 0; q < NBOX; q += 2) {
-          float2 b = *reinterpret_cast<const float2 *>(bx + (long long)idx * NBOX + q);
-          ib[q] = b.x; ib[q + 1] = b.y;
+          for (int q = 0; q < NBOX; q += 2)
+            *reinterpret_cast<float2 *>(&sm.d.cbox[i][q]) = *reinterpret_cast<const float2 *>(bx + (long long)idx * NBOX + q);
         }
+        sm.d.ccls[i] = (int)cl[idx];  // float -> int cast as nms.cu:55-56
+        sm.d.cidx[i] = idx;
       }
-      icls = (int)cl[idx];  // float -> int cast as nms.cu:55-56
-    } else {
+      if (t < kChunk) {
+        sm.d.prevsup[t] = 0;
 #pragma unroll
-      for (int q = 0; q < NBOX; q++) ib[q] = 0.0f;
-    }
-    bool alive = valid;
-    if (w > 0 && alive) {  // suppression by keepers of earlier windows
-      for (int q = 0; q < kept; q++) {
-        if (sm.d.kcls[q] == icls) {
-          float mb[NBOX];
-#pragma unroll
-          for (int c = 0; c < NBOX; c++) mb[c] = sm.d.kbox[q][c];
-          float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
-          if (ov > p.thresh) { alive = false; break; }
-        }
+        for (int w = 0; w < kChunk / 32; w++) sm.d.mask[t][w] = 0u;
       }
-    }
-#pragma unroll
-    for (int q = 0; q < NBOX; q++) sm.d.wbox[t][q] = ib[q];
-    sm.d.wcls[t] = icls;
-    unsigned bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) s_alive[warp] = bal;
-    __syncthreads();
-
-    // greedy over the keepers of this window (nms_kernel, nms.cu:49-79).  Every thread scans
-    // the 32-word survivor bitmap for the next keeper after the barrier; a thread that races
-    // ahead only clears bits ABOVE that keeper, so all threads agree without a second barrier.
-    int m = -1;
-    while (true) {
-      int ww = (m + 1) >> 5;
-      unsigned bits = (ww < 32) ? (s_alive[ww] & (0xffffffffu << ((m + 1) & 31))) : 0u;
-      while (bits == 0u && ++ww < 32) bits = s_alive[ww];
-      if (bits == 0u) break;
-      m = (ww << 5) + __ffs(bits) - 1;
-      if (t == m) {  // the keeper records itself
-#pragma unroll
-        for (int q = 0; q < NBOX; q++) sm.d.kbox[kept][q] = ib[q];
-        sm.d.kcls[kept] = icls;
-        sm.d.kidx[kept] = idx;
-      }
-      kept++;
-      if (kept >= D) break;
-      if (alive && t > m && sm.d.wcls[m] == icls) {
-        float mb[NBOX];
-#pragma unroll
-        for (int q = 0; q < NBOX; q++) mb[q] = sm.d.wbox[m][q];
-        float ov = (NBOX == 4) ? aligned_overlap(ib, mb) : rotated_overlap(ib, mb, p.fixed_angle);
-        if (ov > p.thresh) {
-          alive = false;
-          atomicAnd(&s_alive[warp], ~(1u << lane));
-        }
-      }
-      __syncthreads();
     }
     __syncthreads();
-    if (kept >= D) break;
-
-    // window exhausted: its suppressed candidates, in rank order, extend the output tail
-    if (ntail < D) {
-      bool dead = valid && !alive;
-      unsigned db = __ballot_sync(0xffffffffu, dead);
-      if (lane == 0) s_wsum[warp] = __popc(db);
-      __syncthreads();
-      int woff = 0, tot = 0;
-      for (int q = 0; q < 32; q++) {
-        int v = s_wsum[q];
-        if (q < warp) woff += v;
-        tot += v;
+    // (A) against keepers of earlier chunks: pairs (i, q), i < cn, q < kept
+    for (int pidx = t; pidx < cn * kept; pidx += kThreads) {
+      const int i = pidx % cn, q = pidx / cn;
+      if (sm.d.kcls[q] == sm.d.ccls[i]) {
+        float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.kbox[q])
+                               : rotated_overlap(sm.d.cbox[i], sm.d.kbox[q], p.fixed_angle);
+        if (ov > p.thresh) sm.d.prevsup[i] = 1;
       }
-      int pos = ntail + woff + __popc(db & ((1u << lane) - 1u));
-      if (dead && pos < D) sm.d.tidx[pos] = idx;
-      ntail += tot;
-      __syncthreads();
     }
+    // (B) inside the chunk: pairs (i, j) with j < i; thread -> (i, 16 consecutive j)
+    for (int pidx = t; pidx < cn * (kChunk / 16); pidx += kThreads) {
+      const int i = pidx % cn, jg = pidx / cn;
+      unsigned bits = 0u;
+      const int icls = sm.d.ccls[i];
+#pragma unroll 4
+      for (int jj = 0; jj < 16; jj++) {
+        const int j = jg * 16 + jj;
+        if (j < i && sm.d.ccls[j] == icls) {
+          float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.cbox[j])
+                                 : rotated_overlap(sm.d.cbox[i], sm.d.cbox[j], p.fixed_angle);
+          if (ov > p.thresh) bits |= 1u << jj;
+        }
+      }
+      if (bits) atomicOr(&sm.d.mask[i][jg >> 1], bits << ((jg & 1) * 16));
+    }
+    __syncthreads();
+    // (C) sequential resolution by one warp: lane w (< 4) owns survivor word w of the chunk
+    if (warp == 0) {
+      unsigned surv = 0u;
+      int k2 = kept, nt2 = ntail;
+      for (int i = 0; i < cn && k2 < D; i++) {
+        const unsigned hit = (lane < kChunk / 32) ? (sm.d.mask[i][lane] & surv) : 0u;
+        const bool dead = sm.d.prevsup[i] || __any_sync(0xffffffffu, hit != 0u);
+        if (!dead) {
+          if (lane == (i >> 5)) surv |= 1u << (i & 31);
+          if (lane < NBOX) sm.d.kbox[k2][lane] = sm.d.cbox[i][lane];
+          if (lane == 0) { sm.d.kcls[k2] = sm.d.ccls[i]; sm.d.kidx[k2] = sm.d.cidx[i]; }
+          k2++;
+        } else {
+          if (lane == 0 && nt2 < D) sm.d.tidx[nt2] = sm.d.cidx[i];
+          nt2++;
+        }
+      }
+      if (lane == 0) { s_kept = k2; s_ntail = nt2; }
+    }
+    __syncthreads();
+    kept = s_kept;
+    ntail = s_ntail;
   }
   __syncthreads();
 
