@@ -138,8 +138,12 @@ typedef struct {
   void *y;
   int n, h, width, cin, cout, ksize, relu, out_mode, ldy, ldr;
   int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2) on even h, width; y is [n, h/2, width/2, ...] */
+  const void *bias_op;  /* optional: bias packed by odtk_conv_pack_bias ([cout, 64] fp16).  When given, the
+                           bias is added by ONE extra K block on the tensor core instead of in the epilogue */
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
+/* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */
+int odtk_conv_pack_bias(const float *bias, void *out, int cout, odtk_stream_t stream);
 
 /* Gather the receptive fields of a ksize x ksize / stride / pad convolution over NHWC
  * fp16 x into out[pixels, kpad] (tap-major, channel-minor, zero padded to kpad columns;

@@ -146,7 +146,8 @@ __device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(
 template <int CPW, bool UPS>   // CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmOnes,
+                 const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ ConvParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes + kEpiWarps * kSlabBytes);
@@ -215,6 +216,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
+        if (p.bias_mma) {
+          // one more K block: A = rows of (1, 1, 0, ...), B = (bias_hi, bias_lo, 0, ...) per output channel:
+          // the tensor core adds the fp32 bias (split into two fp16 terms, exact to 2^-22) for free
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          unsigned char *sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + b_bytes);
+          tma_load_2d(sa, &tmOnes, &bars->full[stage], 0, 0);
+          tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -230,12 +241,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
-        for (int kb = 0; kb < kblocks; kb++) {
+        const int kb_total = kblocks + (p.bias_mma ? 1 : 0);
+        for (int kb = 0; kb < kb_total; kb++) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_desc_kmajor(sa, p.row_bytes), db = make_desc_kmajor(sa + kABytes, p.row_bytes);
-          const int ksteps = p.row_bytes >> 5;   // UMMA_K(16) steps per block: +32 B each inside the swizzle atom
+          const int ksteps = (kb == kblocks) ? 1 : (p.row_bytes >> 5);   // UMMA_K(16) steps per block (+32 B each); the bias block has one
           for (int k = 0; k < ksteps; k++)
             tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&bars->empty[stage]);
@@ -333,7 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         };
-        if (p.bias && n_tile != bias_tile) {   // (re)load this warp's bias values: only when the N tile changes
+        if (p.bias && !p.bias_mma && n_tile != bias_tile) {   // (re)load this warp's bias values: only when the N tile changes
           bias_tile = n_tile;
 #pragma unroll
           for (int i = 0; i < 2; i++) {
@@ -385,7 +397,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float f[16];
 #pragma unroll
               for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[cc & 1][j]);
-              if (p.bias) {   // lane l of the warp holds the bias of segment columns l and 32 + l
+              if (p.bias && !p.bias_mma) {   // lane l of the warp holds the bias of segment columns l and 32 + l
                 const float bsrc = (cc & 2) ? (si ? breg[1][1] : breg[0][1]) : (si ? breg[1][0] : breg[0][0]);
 #pragma unroll
                 for (int j = 0; j < 16; j++) f[j] += __shfl_sync(0xffffffffu, bsrc, (cc & 1) * 16 + j);
@@ -401,16 +413,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
                 }
               }
-              if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.0f);
-              }
               uint4 o0, o1;
               __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
 #pragma unroll
               for (int j = 0; j < 4; j++) {
                 q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
                 q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+              }
+              if (p.relu) {   // on the packed halves: max(round(x), 0) == round(max(x, 0)), half the instructions
+                const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
               }
               *reinterpret_cast<uint4 *>(srow + u0) = o0;
               *reinterpret_cast<uint4 *>(srow + u1) = o1;
@@ -467,7 +480,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; j++) {
             if (j < ncol) {
-              float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.0f);
+              float x = __uint_as_float(v[j]) + ((p.bias && !p.bias_mma) ? __ldg(p.bias + col0 + j) : 0.0f);
               if (p.relu) x = fmaxf(x, 0.0f);
               if (p.out_mode == ODTK_OUT_NCHW_F32_SIGMOID) x = sigmoidf_accurate(x);
               o[j * cs] = x;
@@ -548,12 +561,39 @@ bool configure_kernels() {
   return configure_one<1, false>() && configure_one<2, false>() && configure_one<4, false>() && configure_one<4, true>();
 }
 void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                 const ConvParams &p) {
+                 const CUtensorMap &tmO, const CUtensorMap &tmBi, const ConvParams &p) {
   const int nchunks = p.BN >> 4;
-  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
-  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
-  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
-  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
+  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
+  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
+  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
+}
+
+// constant A operand of the bias block: 128 rows x 64 fp16, columns 0 and 1 are 1.0
+__device__ __half g_ones_op[128 * 64];
+__global__ void init_ones_kernel() {
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_ones_op[i] = __float2half_rn((i & 63) < 2 ? 1.0f : 0.0f);
+}
+// bias operand: [cout, 64] fp16 with (hi, lo, 0, ...): hi + lo == bias to 2^-22 relative
+__global__ void pack_bias_kernel(const float *bias, __half *out, int cout) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout * 64; i += gridDim.x * blockDim.x) {
+    const int c = i >> 6, k = i & 63;
+    float v = 0.0f;
+    if (k < 2) {
+      const float b = bias[c];
+      const float hi = __half2float(__float2half_rn(b));
+      v = (k == 0) ? hi : b - hi;
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+const void *ones_operand(cudaStream_t stream) {
+  static void *ptr = nullptr;
+  if (!ptr) {
+    if (cudaGetSymbolAddress(&ptr, g_ones_op) != cudaSuccess) return nullptr;
+    init_ones_kernel<<<1, 256, 0, stream>>>();
+  }
+  return ptr;
 }
 
 }  // namespace
@@ -663,11 +703,23 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     uint32_t box[2] = {64, 32};
     if (encode_map(&tmC, d->y, 2, dims, str, box)) p.tma_store = 1;
   }
+  CUtensorMap tmOnes = tmB, tmBias = tmB;
+  static int bias_mma_on = -1;
+  if (bias_mma_on < 0) { const char *e = getenv("ODTK_CONV_BIAS_MMA"); bias_mma_on = e ? atoi(e) : 1; }
+  if (bias_mma_on && d->bias_op && d->bias) {
+    const void *ones = ones_operand(stream);
+    uint64_t dimsO[2] = {64, 128}, strO[1] = {128};
+    uint32_t boxO[2] = {64, 128};
+    uint64_t dimsB[2] = {64, (uint64_t)d->cout}, strB[1] = {128};
+    uint32_t boxB[2] = {64, (uint32_t)BN};
+    if (ones && encode_map(&tmOnes, ones, 2, dimsO, strO, boxO) && encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB))
+      p.bias_mma = 1;
+  }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    launch_conv(grid, stream, tmA, tmB, tmC, p);
+    launch_conv(grid, stream, tmA, tmB, tmC, tmOnes, tmBias, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
@@ -725,7 +777,14 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    launch_conv(grid, stream, tmA, tmB, tmB, p);
+    launch_conv(grid, stream, tmA, tmB, tmB, tmB, tmB, p);
   }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+// Pack a fp32 bias vector into the [cout, 64] fp16 operand of the bias K block (see odtk_conv_t.bias_op).
+extern "C" int odtk_conv_pack_bias(const float *bias, void *out, int cout, odtk_stream_t stream_) {
+  if (!bias || !out || cout <= 0) return ODTK_E_INVALID;
+  pack_bias_kernel<<<(cout * 64 + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(bias, (__half *)out, cout);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

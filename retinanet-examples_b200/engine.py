@@ -19,7 +19,7 @@ class ConvDesc(ctypes.Structure):
                 ("residual", ctypes.c_void_p), ("upsample", ctypes.c_void_p), ("y", ctypes.c_void_p),
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
                 ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
-                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int)]
+                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int), ("bias_op", ctypes.c_void_p)]
 
 
 def _stream():
@@ -43,8 +43,16 @@ def pack_weight(weight, kpad=None):
     return w.to(torch.float16).contiguous()
 
 
+def pack_bias(bias):
+    """fp32 bias [Cout] (CUDA) -> the [Cout, 64] fp16 operand of the kernel's bias K block."""
+    out = torch.empty((bias.numel(), 64), dtype=torch.float16, device=bias.device)
+    _lib.check(_lib.lib().odtk_conv_pack_bias(ctypes.c_void_p(bias.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                              bias.numel(), _stream()), "conv_pack_bias")
+    return out
+
+
 def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None,
-           stride=1):
+           stride=1, bias_op=None):
     """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
     Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
     assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
@@ -62,6 +70,7 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     d.upsample = upsample.data_ptr() if upsample is not None else None
     d.n, d.h, d.width, d.cin, d.cout, d.ksize = n, h, wd, cin, cout, ksize
     d.relu, d.out_mode, d.ldy, d.ldr, d.stride = int(relu), out_mode, 0, 0, int(stride)
+    d.bias_op = bias_op.data_ptr() if bias_op is not None else None
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
     STATS["launches"] += 1
     return out

@@ -100,6 +100,7 @@ class _Conv:
         self.kpad = kreal if self.direct else (kreal + 63) // 64 * 64
         self.w = engine.pack_weight(weight, self.kpad).to(device)
         self.b = bias.float().contiguous().to(device) if bias is not None else None
+        self.bop = engine.pack_bias(self.b) if self.b is not None else None     # bias as a tensor-core K block
 
     def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False):
         oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
@@ -108,13 +109,14 @@ class _Conv:
             return engine.stem_conv(x, self.w_stem, self.b, self.cout, relu)
         if self.direct:
             assert not in_relu
-            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode)
+            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode, bias_op=self.bop)
         if (self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and not in_relu and upsample is None
                 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0):
             # even-sized stride-2 convolution: strided TMA view, no gather pre-pass
-            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2)
+            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2,
+                                 bias_op=self.bop)
         low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
-        return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode)
+        return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode, bias_op=self.bop)
 
 
 class Model:

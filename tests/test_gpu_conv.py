@@ -127,3 +127,20 @@ def test_strided_conv_direct_tma(n, h, w, cin, cout, ks):
     x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.03), torch.randn(cout, generator=g)
     y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, ks, relu=True, stride=2)
     _close16(y, _ref_conv(x, wt, b, ks, relu=True, stride=2, pad=ks // 2))
+
+
+@pytest.mark.parametrize("ks,cin,cout,mode", [(1, 64, 256, 0), (3, 256, 256, 0), (1, 256, 64, 0), (3, 256, 720, 2), (1, 512, 2048, 0)])
+def test_bias_added_on_the_tensor_core_equals_epilogue_bias(ks, cin, cout, mode):
+    """bias as an extra K block (hi/lo fp16 split, exact to 2^-22) vs the fp32 epilogue add."""
+    g = torch.Generator().manual_seed(cout + ks)
+    n, h, w = 2, 13, 20
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.03), torch.randn(cout, generator=g) * 3
+    pw, bd = engine.pack_weight(wt.float()).to(DEV), b.to(DEV)
+    res = _rand((n, h, w, cout), g).to(DEV) if mode == 0 else None
+    y0 = engine.conv2d(x.to(DEV), pw, bd, cout, ks, relu=(mode == 0), residual=res, out_mode=mode)
+    y1 = engine.conv2d(x.to(DEV), pw, bd, cout, ks, relu=(mode == 0), residual=res, out_mode=mode, bias_op=engine.pack_bias(bd))
+    if mode == 0:
+        assert (y0.float() - y1.float()).abs().max().item() <= 2e-3 * y0.float().abs().max().item()   # <= 1 fp16 ulp flips
+        _close16(y1, _ref_conv(x, wt, b, ks, relu=True, residual=res.cpu()))
+    else:
+        np.testing.assert_allclose(y1.cpu().numpy(), y0.cpu().numpy(), rtol=2e-5, atol=2e-6)
