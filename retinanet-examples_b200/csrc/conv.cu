@@ -130,11 +130,24 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, int row_byt
   return d;
 }
 
+// MN-major operand (N contiguous), 128-byte swizzle: 64-element (128 B) chunks along N are `lbo` bytes apart,
+// 8-row groups along K are 1024 B apart.  Used for the residual tile read as the B operand of I * R.
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 struct Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full, res_empty, ident_full;   // residual-on-the-tensor-core path
   uint32_t tmem_base;
 };
 
@@ -147,7 +160,8 @@ template <int CPW, bool UPS>   // CPW: 16-column chunks per epilogue segment (1,
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmOnes,
-                 const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmIdent, const __grid_constant__ ConvParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes + kEpiWarps * kSlabBytes);
@@ -162,6 +176,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 32 * kEpiWarps); }
+    mbar_init(&bars->res_full, 1); mbar_init(&bars->res_empty, 1); mbar_init(&bars->ident_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -183,7 +198,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, rphase = 0;
+      unsigned char *sres = smem + 2 * (kABytes + kBBytesMax);          // 64 KB residual tile (res_mma: 2 stages only)
+      unsigned char *sident = sres + 4 * kABytes;                        // 32 KB identity
+      if (p.res_mma) {
+        mbar_arrive_expect_tx(&bars->ident_full, 2u * kABytes);
+        tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
+        tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
         const int n0 = n_tile * p.BN;
@@ -226,6 +248,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (p.res_mma) {
+          // residual tile [128 pixels x 256 channels] as four 128B-swizzled 64-channel slices: it becomes the
+          // MN-major B operand of D += I * R (identity times residual), i.e. the tensor core does the add
+          mbar_wait(&bars->res_empty, rphase ^ 1u);
+          mbar_arrive_expect_tx(&bars->res_full, 4u * kABytes);
+#pragma unroll
+          for (int j = 0; j < 4; j++) tma_load_2d(sres + j * kABytes, &tmRes, &bars->res_full, n0 + 64 * j, m_tile * 128);
+          rphase ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
@@ -234,8 +265,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // instruction descriptor: D=f32, A=B=f16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, rphase = 0;
       int it = 0;
+      const uint32_t sres = smem_u32(smem + 2 * (kABytes + kBBytesMax)), sident = sres + 4 * kABytes;
+      if (p.res_mma) mbar_wait(&bars->ident_full, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
         const int buf = it & 1;
         mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -252,6 +285,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (p.res_mma) {
+          mbar_wait(&bars->res_full, rphase);
+          tc_fence_after();
+          rphase ^= 1u;
+          const uint32_t idesc_r = idesc | (1u << 16);     // B operand MN-major
+#pragma unroll
+          for (int j = 0; j < 8; j++) {   // K = 128 pixels of the tile, 16 per instruction
+            const uint64_t da = make_desc_kmajor(sident + (uint32_t)(j >> 2) * kABytes, 128) + (uint64_t)(2 * (j & 3));
+            const uint64_t db = make_desc_mnmajor(sres + (uint32_t)j * 2048u, (uint32_t)kABytes);
+            tc_mma_f16(tmem_d, da, db, idesc_r, 1u);
+          }
+          tc_commit(&bars->res_empty);
         }
         tc_commit(&bars->tmem_full[buf]);
       }
@@ -278,7 +324,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = lane >> lsh, lx = lane & (lpr - 1);
     const int nsegs = (nchunks + cpw - 1) / cpw;
     const bool nhwc = p.out_mode == ODTK_OUT_NHWC_F16;
-    const bool has_addend = p.residual != nullptr || (UPS && p.upsample != nullptr);
+    const bool has_addend = (p.residual != nullptr && !p.res_mma) || (UPS && p.upsample != nullptr);
     const int hw = p.H * p.W, per_img = p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
     // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
     int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
@@ -332,7 +378,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < 8; k++) {
             dst[k] = make_uint4(0u, 0u, 0u, 0u);
             if (pix8[k] >= 0 && lane_on) {
-              if (p.residual) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
+              if (p.residual && !p.res_mma) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
               if (UPS && p.upsample) {
                 const int i2 = pix8[k] / hw, rem = pix8[k] - i2 * hw, h2 = rem / p.W, w2 = rem - h2 * p.W;
                 const long long up = ((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1);
@@ -561,12 +607,27 @@ bool configure_kernels() {
   return configure_one<1, false>() && configure_one<2, false>() && configure_one<4, false>() && configure_one<4, true>();
 }
 void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-                 const CUtensorMap &tmO, const CUtensorMap &tmBi, const ConvParams &p) {
+                 const CUtensorMap &tmO, const CUtensorMap &tmBi, const CUtensorMap &tmR, const CUtensorMap &tmI,
+                 const ConvParams &p) {
   const int nchunks = p.BN >> 4;
-  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
-  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
-  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
-  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, p);
+  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+}
+
+// constant A operand of the residual MMAs: the 128 x 128 identity
+__device__ __half g_ident_op[128 * 128];
+__global__ void init_ident_kernel() {
+  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) g_ident_op[i] = __float2half_rn((i >> 7) == (i & 127) ? 1.0f : 0.0f);
+}
+const void *ident_operand(cudaStream_t stream) {
+  static void *ptr = nullptr;
+  if (!ptr) {
+    if (cudaGetSymbolAddress(&ptr, g_ident_op) != cudaSuccess) return nullptr;
+    init_ident_kernel<<<1, 256, 0, stream>>>();
+  }
+  return ptr;
 }
 
 // constant A operand of the bias block: 128 rows x 64 fp16, columns 0 and 1 are 1.0
@@ -715,11 +776,27 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     if (ones && encode_map(&tmOnes, ones, 2, dimsO, strO, boxO) && encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB))
       p.bias_mma = 1;
   }
+  // residual add on the tensor core (D += I * R): wide 1x1 residual layers (bottleneck conv3)
+  CUtensorMap tmRes = tmB, tmIdent = tmB;
+  static int res_mma_on = -1;
+  if (res_mma_on < 0) { const char *e = getenv("ODTK_CONV_RES_MMA"); res_mma_on = e ? atoi(e) : 1; }
+  if (res_mma_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN == 256 && d->cout % 256 == 0 &&
+      (p.ldr % 8) == 0 && (((uintptr_t)d->residual) & 15) == 0) {
+    const void *ident = ident_operand(stream);
+    uint64_t dimsR[2] = {(uint64_t)p.ldr, (uint64_t)p.M}, strR[1] = {(uint64_t)p.ldr * 2};
+    uint32_t boxR[2] = {64, 128};
+    uint64_t dimsI[2] = {128, 128}, strI[1] = {256};
+    uint32_t boxI[2] = {64, 128};
+    if (ident && encode_map(&tmRes, d->residual, 2, dimsR, strR, boxR) && encode_map(&tmIdent, ident, 2, dimsI, strI, boxI)) {
+      p.res_mma = 1;
+      p.nstages = 2;   // the rest of the pipeline region holds the residual tile (64 KB) and the identity (32 KB)
+    }
+  }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    launch_conv(grid, stream, tmA, tmB, tmC, tmOnes, tmBias, p);
+    launch_conv(grid, stream, tmA, tmB, tmC, tmOnes, tmBias, tmRes, tmIdent, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
@@ -777,7 +854,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   const int grid = total < g_num_sms ? total : g_num_sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    launch_conv(grid, stream, tmA, tmB, tmB, tmB, tmB, p);
+    launch_conv(grid, stream, tmA, tmB, tmB, tmB, tmB, tmB, tmB, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
