@@ -92,10 +92,30 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {   // arrive on the same barrier in every CTA of `mask`
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -156,7 +176,7 @@ struct Barriers {
 __device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int CPW, bool UPS>   // CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
+template <int CPW, bool UPS, bool CL2>   // CL2: 2-CTA cluster sharing the weight tile through TMA multicast; CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmOnes,
@@ -174,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL2 ? 2 : 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 32 * kEpiWarps); }
     mbar_init(&bars->res_full, 1); mbar_init(&bars->res_empty, 1); mbar_init(&bars->ident_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -185,11 +205,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL2) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work items: single tiles, or -- in a 2-CTA cluster -- pairs of consecutive M tiles on the same N tile (both CTAs
+  // run the same K loop in lockstep and each loads half of the weight tile for both)
+  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  const int mpairs = (p.num_m_tiles + 1) >> 1;
+  const int w_first = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = CL2 ? mpairs * p.num_n_tiles : total_tiles;
+  auto work_tile = [&](int wi, int &m_tile, int &n_tile) -> bool {   // returns false for the padding tile of an odd pair
+    if (CL2) {
+      n_tile = wi / mpairs;
+      m_tile = 2 * (wi - n_tile * mpairs) + crank;
+      if (m_tile >= p.num_m_tiles) { m_tile = p.num_m_tiles - 1; return false; }
+      return true;
+    }
+    m_tile = wi % p.num_m_tiles;
+    n_tile = wi / p.num_m_tiles;
+    return true;
+  };
   const int kblocks = p.taps * p.kblocks_per_tap;
   const uint32_t a_bytes = (p.mode == 0) ? (uint32_t)(128 * p.row_bytes) : (uint32_t)(p.TH * p.TW * p.row_bytes);
   const uint32_t b_bytes = (uint32_t)(p.BN * p.row_bytes);
@@ -206,8 +244,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
         tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      for (int tile = w_first; tile < w_total; tile += w_step) {
+        int m_tile, n_tile;
+        work_tile(tile, m_tile, n_tile);
         const int n0 = n_tile * p.BN;
         int img = 0, h0 = 0, w0 = 0;
         if (p.mode != 0) {
@@ -234,7 +273,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
             else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
-            tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
+            if (CL2) {   // each CTA fetches half of the weight rows and multicasts them to both
+              const int half = p.BN >> 1;
+              tma_load_2d_mc(sb + crank * half * p.row_bytes, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems,
+                             n0 + crank * half, (uint16_t)3);
+            } else {
+              tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -245,7 +290,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           unsigned char *sa = smem + stage * kStageBytes;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + b_bytes);
           tma_load_2d(sa, &tmOnes, &bars->full[stage], 0, 0);
-          tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
+          if (CL2) tma_load_2d_mc(sa + kABytes + crank * (p.BN >> 1) * 128, &tmBias, &bars->full[stage], 0, n0 + crank * (p.BN >> 1), (uint16_t)3);
+          else     tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_mma) {
@@ -269,7 +315,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       const uint32_t sres = smem_u32(smem + 2 * (kABytes + kBBytesMax)), sident = sres + 4 * kABytes;
       if (p.res_mma) mbar_wait(&bars->ident_full, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      for (int tile = w_first; tile < w_total; tile += w_step, it++) {
         const int buf = it & 1;
         mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -283,7 +329,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int ksteps = (kb == kblocks) ? 1 : (p.row_bytes >> 5);   // UMMA_K(16) steps per block (+32 B each); the bias block has one
           for (int k = 0; k < ksteps; k++)
             tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          tc_commit(&bars->empty[stage]);
+          if (CL2) tc_commit_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_mma) {
@@ -342,11 +388,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int bias_tile = -1;
     static_assert(kEpiWarps == 8 || kEpiWarps == 16, "bias registers assume <= 2 segments per warp");
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+    for (int tile = w_first; tile < w_total; tile += w_step, it++) {
       const int buf = it & 1;
-      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      int m_tile, n_tile;
+      const bool real_tile = work_tile(tile, m_tile, n_tile);
       const int n0 = n_tile * p.BN;
-      const bool active = nhwc ? (sg < nsegs) : (sg < nchunks);
+      const bool active = real_tile && (nhwc ? (sg < nsegs) : (sg < nchunks));
       mbar_wait(&bars->tmem_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
@@ -417,11 +464,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (k < lpr) *reinterpret_cast<uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)) = pre[k];
             __syncwarp();
             if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, n0, pre);
-            else if (p.tma_store && tile + (int)gridDim.x < total_tiles) {
+            else if (p.tma_store && !CL2 && tile + w_step < w_total) {
               // last segment of this tile: the write-out below goes through the TMA unit and no longer
               // needs pix8, so fetch the addend of the NEXT tile's first segment now -- its DRAM latency
               // then overlaps this segment's maths and the wait for the next accumulator
-              const int nt = tile + (int)gridDim.x, m2 = nt % p.num_m_tiles, n2 = nt / p.num_m_tiles;
+              const int nt = tile + w_step, m2 = nt % p.num_m_tiles, n2 = nt / p.num_m_tiles;
 #pragma unroll
               for (int k = 0; k < 8; k++) {
                 const int m = m2 * 128 + dw8[k];
@@ -541,7 +588,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL2) cluster_sync_all(); else __syncthreads();   // no CTA may leave while its peer can still write to it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -598,22 +645,42 @@ void choose_patch(int H, int W, int &TH, int &TW) {
 
 int g_num_sms = 0;
 
-template <int CPW, bool UPS>
+template <int CPW, bool UPS, bool CL2>
 bool configure_one() {
-  return cudaFuncSetAttribute(conv_gemm_kernel<CPW, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) ==
+  return cudaFuncSetAttribute(conv_gemm_kernel<CPW, UPS, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) ==
          cudaSuccess;
 }
 bool configure_kernels() {
-  return configure_one<1, false>() && configure_one<2, false>() && configure_one<4, false>() && configure_one<4, true>();
+  return configure_one<1, false, false>() && configure_one<2, false, false>() && configure_one<4, false, false>() &&
+         configure_one<4, true, false>() && configure_one<4, false, true>();
+}
+template <int CPW, bool UPS, bool CL2, class... Args>
+void launch_one(int grid, cudaStream_t stream, Args... args) {
+  if (!CL2) {
+    conv_gemm_kernel<CPW, UPS, CL2><<<grid, kThreads, kSmemBytes, stream>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv_gemm_kernel<CPW, UPS, CL2>, args...);
 }
 void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
                  const CUtensorMap &tmO, const CUtensorMap &tmBi, const CUtensorMap &tmR, const CUtensorMap &tmI,
                  const ConvParams &p) {
   const int nchunks = p.BN >> 4;
-  if (p.upsample)        conv_gemm_kernel<4, true><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (nchunks <= 4) conv_gemm_kernel<1, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (nchunks <= 8) conv_gemm_kernel<2, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else                   conv_gemm_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  if (p.cluster2)        launch_one<4, false, true>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (p.upsample)   launch_one<4, true, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 4) launch_one<1, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 8) launch_one<2, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else                   launch_one<4, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
 }
 
 // constant A operand of the residual MMAs: the 128 x 128 identity
@@ -775,6 +842,23 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     uint32_t boxB[2] = {64, (uint32_t)BN};
     if (ones && encode_map(&tmOnes, ones, 2, dimsO, strO, boxO) && encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB))
       p.bias_mma = 1;
+  }
+  // 2-CTA clusters with weight multicast: the compute-bound 256-wide layers with enough tiles for every cluster
+  static int cluster_on = -1;
+  if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 1; }
+  if (cluster_on && BN > 128 && !d->upsample && !d->residual && (p.mode == 0 || p.mode == 1 || p.mode == 3) &&
+      ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
+    const uint64_t Kw = (uint64_t)p.taps * d->cin;
+    uint64_t dims[2] = {Kw, (uint64_t)d->cout}, str[1] = {Kw * 2};
+    uint32_t box[2] = {64, (uint32_t)(BN / 2)};
+    bool ok = encode_map(&tmB, d->w, 2, dims, str, box);
+    if (ok && p.bias_mma) {
+      uint64_t dimsB[2] = {64, (uint64_t)d->cout}, strB[1] = {128};
+      uint32_t boxB[2] = {64, (uint32_t)(BN / 2)};
+      ok = encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB);
+    }
+    if (ok) { p.cluster2 = 1; p.tma_store = 0; }
+    else return ODTK_E_CUDA;
   }
   // residual add on the tensor core (D += I * R): wide 1x1 residual layers (bottleneck conv3)
   CUtensorMap tmRes = tmB, tmIdent = tmB;

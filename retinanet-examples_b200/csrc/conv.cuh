@@ -16,6 +16,7 @@ struct ConvParams {
   void *out;
   int relu, out_mode, ldy, ldr, up_h, up_w;
   int row_bytes;        // bytes of one K block row in shared memory: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, stem)
+  int cluster2;         // launched as 2-CTA clusters: each CTA loads half of the weight tile and multicasts it
   int res_mma;          // the residual is added by the tensor core: D += I * R (mode 0, BN = 256)
   int bias_mma;         // the bias is added by one extra K block on the tensor core (A = ones, B = bias hi/lo)
   int tma_store;        // epilogue hands 32x64 slabs to cp.async.bulk.tensor stores (mode 0, BN > 128)

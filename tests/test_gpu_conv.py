@@ -144,3 +144,20 @@ def test_bias_added_on_the_tensor_core_equals_epilogue_bias(ks, cin, cout, mode)
         _close16(y1, _ref_conv(x, wt, b, ks, relu=True, residual=res.cpu()))
     else:
         np.testing.assert_allclose(y1.cpu().numpy(), y0.cpu().numpy(), rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ks", [(1, 100, 160, 256, 512, 3), (4, 100, 160, 256, 256, 3), (2, 200, 320, 64, 256, 1),
+                                              (3, 100, 160, 128, 720, 3)])
+def test_cluster_multicast_path(n, h, w, cin, cout, ks):
+    """Shapes with enough 256-wide tiles to run as 2-CTA clusters (weight tile multicast), incl. an odd
+    number of M tiles (padding tile of the last pair) and the fp32 NCHW head epilogue."""
+    g = torch.Generator().manual_seed(n * 31 + cout)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.03), torch.randn(cout, generator=g)
+    bd = b.to(DEV)
+    if cout == 720:
+        y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, out_mode=engine.OUT_NCHW_F32,
+                          bias_op=engine.pack_bias(bd))
+        np.testing.assert_allclose(y.cpu().numpy(), _ref_conv(x, wt, b, ks).numpy(), rtol=2e-4, atol=2e-4)
+    else:
+        y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=True, bias_op=engine.pack_bias(bd))
+        _close16(y, _ref_conv(x, wt, b, ks, relu=True))
