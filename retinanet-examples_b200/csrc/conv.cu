@@ -98,6 +98,33 @@ __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cta_group::2 TMA loads: destination in the executing CTA, completion counted on a barrier that may live in the peer
+__device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -117,6 +144,19 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {   /
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar, uint16_t mask) {   // cta_group::2 commit, arrives in every CTA of `mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -176,7 +216,7 @@ struct Barriers {
 __device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int CPW, bool UPS, bool CL2>   // CL2: 2-CTA cluster sharing the weight tile through TMA multicast; CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
+template <int CPW, bool UPS, int CL>   // CL: 0 = single CTAs; 1 = 2-CTA cluster, weight tile multicast; 2 = 2-CTA cluster, cta_group::2 MMA (M = 256 per pair, each CTA holds half of the weight tile); CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmOnes,
@@ -185,7 +225,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes + kEpiWarps * kSlabBytes);
-  const int kStages = p.nstages, kStageBytes = kABytes + p.BN * 128;   // per-layer pipeline geometry
+  constexpr bool CL2 = (CL == 1), TWO = (CL == 2), CLUSTER = (CL != 0);
+  const int kStages = p.nstages, kStageBytes = kABytes + (TWO ? p.BN >> 1 : p.BN) * 128;   // per-layer pipeline geometry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -195,30 +236,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL2 ? 2 : 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 32 * kEpiWarps); }
+    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], (TWO ? 2 : 1) * 32 * kEpiWarps); }
     mbar_init(&bars->res_full, 1); mbar_init(&bars->res_empty, 1); mbar_init(&bars->ident_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                 "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (TWO) {   // both CTAs of the pair issue the paired allocation from the same warp id
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
-  if (CL2) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any multicast / remote arrive
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   // work items: single tiles, or -- in a 2-CTA cluster -- pairs of consecutive M tiles on the same N tile (both CTAs
   // run the same K loop in lockstep and each loads half of the weight tile for both)
-  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
   const int mpairs = (p.num_m_tiles + 1) >> 1;
-  const int w_first = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int w_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int w_total = CL2 ? mpairs * p.num_n_tiles : total_tiles;
+  const int w_first = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = CLUSTER ? mpairs * p.num_n_tiles : total_tiles;
   auto work_tile = [&](int wi, int &m_tile, int &n_tile) -> bool {   // returns false for the padding tile of an odd pair
-    if (CL2) {
+    if (CLUSTER) {
       n_tile = wi / mpairs;
       m_tile = 2 * (wi - n_tile * mpairs) + crank;
       if (m_tile >= p.num_m_tiles) { m_tile = p.num_m_tiles - 1; return false; }
@@ -230,7 +277,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   };
   const int kblocks = p.taps * p.kblocks_per_tap;
   const uint32_t a_bytes = (p.mode == 0) ? (uint32_t)(128 * p.row_bytes) : (uint32_t)(p.TH * p.TW * p.row_bytes);
-  const uint32_t b_bytes = (uint32_t)(p.BN * p.row_bytes);
+  const uint32_t b_bytes = (uint32_t)((TWO ? p.BN >> 1 : p.BN) * p.row_bytes);   // weight bytes landing in THIS CTA per K block
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -262,8 +309,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             unsigned char *sa = smem + stage * kStageBytes;
             unsigned char *sb = sa + kABytes;
-            mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
             const int kelems = p.row_bytes >> 1;   // K elements per block: 64 (SW128) or 32 (SW64)
+            if (TWO) {
+              // cta_group::2: both CTAs load their own A rows and their half of the weight rows into their own
+              // shared memory; every byte is counted on the LEADER's barrier, which the leader arms for the pair
+              const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (a_bytes + b_bytes));
+              const int half = p.BN >> 1;
+              if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, w0 + dx, h0 + dy, img);
+              else if (p.mode == 3) {
+                const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
+                tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
+              } else                tma2_load_2d(sa, &tmA, lbar, kb * 64, m_tile * 128);
+              tma2_load_2d(sb, &tmB, lbar, (tap * p.kblocks_per_tap + kb) * kelems, n0 + crank * half);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+            mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
             if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
             else if (p.mode == 3) {
               // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
@@ -288,10 +350,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // the tensor core adds the fp32 bias (split into two fp16 terms, exact to 2^-22) for free
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           unsigned char *sa = smem + stage * kStageBytes;
+          if (TWO) {
+            const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * ((uint32_t)kABytes + b_bytes));
+            tma2_load_2d(sa, &tmOnes, lbar, 0, 0);
+            tma2_load_2d(sa + kABytes, &tmBias, lbar, 0, n0 + crank * (p.BN >> 1));
+          } else {
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + b_bytes);
           tma_load_2d(sa, &tmOnes, &bars->full[stage], 0, 0);
           if (CL2) tma_load_2d_mc(sa + kABytes + crank * (p.BN >> 1) * 128, &tmBias, &bars->full[stage], 0, n0 + crank * (p.BN >> 1), (uint16_t)3);
           else     tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_mma) {
@@ -307,9 +376,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (lane == 0 && (!TWO || crank == 0)) {   // cta_group::2: the leader CTA issues for the pair
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N = BN, M = 128 (256 across a CTA pair)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, rphase = 0;
       int it = 0;
@@ -327,9 +396,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_desc_kmajor(sa, p.row_bytes), db = make_desc_kmajor(sa + kABytes, p.row_bytes);
           const int ksteps = (kb == kblocks) ? 1 : (p.row_bytes >> 5);   // UMMA_K(16) steps per block (+32 B each); the bias block has one
-          for (int k = 0; k < ksteps; k++)
-            tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          if (CL2) tc_commit_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+          for (int k = 0; k < ksteps; k++) {
+            if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          if (TWO)      tc_commit2_mc(&bars->empty[stage], (uint16_t)3);
+          else if (CL2) tc_commit_mc(&bars->empty[stage], (uint16_t)3);
+          else          tc_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_mma) {
@@ -345,7 +418,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tc_commit(&bars->res_empty);
         }
-        tc_commit(&bars->tmem_full[buf]);
+        if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -464,7 +537,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (k < lpr) *reinterpret_cast<uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)) = pre[k];
             __syncwarp();
             if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, n0, pre);
-            else if (p.tma_store && !CL2 && tile + w_step < w_total) {
+            else if (p.tma_store && !CLUSTER && tile + w_step < w_total) {
               // last segment of this tile: the write-out below goes through the TMA unit and no longer
               // needs pix8, so fetch the addend of the NEXT tile's first segment now -- its DRAM latency
               // then overlaps this segment's maths and the wait for the next accumulator
@@ -582,16 +655,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[buf]);
+      if (TWO) mbar_arrive_remote(mapa_rank(smem_u32(&bars->tmem_empty[buf]), 0));   // the leader waits for both CTAs
+      else     mbar_arrive(&bars->tmem_empty[buf]);
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
-  if (CL2) cluster_sync_all(); else __syncthreads();   // no CTA may leave while its peer can still write to it
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();   // no CTA may leave while its peer can still write to it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    else     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
@@ -645,16 +720,16 @@ void choose_patch(int H, int W, int &TH, int &TW) {
 
 int g_num_sms = 0;
 
-template <int CPW, bool UPS, bool CL2>
+template <int CPW, bool UPS, int CL2>
 bool configure_one() {
   return cudaFuncSetAttribute(conv_gemm_kernel<CPW, UPS, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) ==
          cudaSuccess;
 }
 bool configure_kernels() {
-  return configure_one<1, false, false>() && configure_one<2, false, false>() && configure_one<4, false, false>() &&
-         configure_one<4, true, false>() && configure_one<4, false, true>();
+  return configure_one<1, false, 0>() && configure_one<2, false, 0>() && configure_one<4, false, 0>() &&
+         configure_one<4, true, 0>() && configure_one<4, false, 1>() && configure_one<4, false, 2>();
 }
-template <int CPW, bool UPS, bool CL2, class... Args>
+template <int CPW, bool UPS, int CL2, class... Args>
 void launch_one(int grid, cudaStream_t stream, Args... args) {
   if (!CL2) {
     conv_gemm_kernel<CPW, UPS, CL2><<<grid, kThreads, kSmemBytes, stream>>>(args...);
@@ -676,11 +751,12 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
                  const CUtensorMap &tmO, const CUtensorMap &tmBi, const CUtensorMap &tmR, const CUtensorMap &tmI,
                  const ConvParams &p) {
   const int nchunks = p.BN >> 4;
-  if (p.cluster2)        launch_one<4, false, true>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (p.upsample)   launch_one<4, true, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (nchunks <= 4) launch_one<1, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (nchunks <= 8) launch_one<2, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else                   launch_one<4, false, false>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  if (p.cluster2 == 2)   launch_one<4, false, 2>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (p.cluster2)   launch_one<4, false, 1>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (p.upsample)   launch_one<4, true, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 4) launch_one<1, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= 8) launch_one<2, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else                   launch_one<4, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
 }
 
 // constant A operand of the residual MMAs: the 128 x 128 identity
@@ -845,7 +921,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   }
   // 2-CTA clusters with weight multicast: the compute-bound 256-wide layers with enough tiles for every cluster
   static int cluster_on = -1;
-  if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 1; }
+  if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 2; }   // 0 off, 1 multicast, 2 cta_group::2
   if (cluster_on && BN > 128 && !d->upsample && !d->residual && (p.mode == 0 || p.mode == 1 || p.mode == 3) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
@@ -857,7 +933,11 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
       uint32_t boxB[2] = {64, (uint32_t)(BN / 2)};
       ok = encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB);
     }
-    if (ok) { p.cluster2 = 1; p.tma_store = 0; }
+    if (ok) {
+      p.cluster2 = cluster_on >= 2 ? 2 : 1;
+      p.tma_store = 0;
+      if (p.cluster2 == 2) { p.nstages = kPipeBytes / (kABytes + BN * 64); if (p.nstages > kMaxStages) p.nstages = kMaxStages; }
+    }
     else return ODTK_E_CUDA;
   }
   // residual add on the tensor core (D += I * R): wide 1x1 residual layers (bottleneck conv3)
