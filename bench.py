@@ -136,7 +136,9 @@ class FullWorkload:
         engine.STATS["launches"] = engine.STATS["conv_flops"] = 0
         self.model.forward(self.dev_x)            # eager pass: counts launches / algorithmic FLOPs
         torch.cuda.synchronize()
-        self.launches_per_step = engine.STATS["launches"] + 4       # + decode (3) + nms (1)
+        # + decode (filter, gather, select: the filter launch disappears when the class head's last
+        #   convolution appends the candidates itself) + nms (1); memsets are not counted
+        self.launches_per_step = engine.STATS["launches"] + (3 if self.model.fused_candidates else 4)
         self.flops_per_step = engine.STATS["conv_flops"]
 
     def _gather(self, out):

@@ -90,6 +90,32 @@ long long odtk_decode_levels(int batch, int num_levels, const odtk_level_t *leve
                              int nbox, void *const *outputs, size_t out_stride, size_t out_offset,
                              void *workspace, size_t workspace_size, odtk_stream_t stream);
 
+/* Fused class-head path (B200-native): the last class-head convolution appends its above-threshold
+ * scores straight to the decode workspace (odtk_conv2d with out_mode ODTK_OUT_CANDIDATES and the level's
+ * sink) instead of writing the dense [B, A*C, H, W] score map that odtk_decode_levels would stream
+ * through again.  odtk_decode_fused_begin lays out `workspace` (query the size with workspace == NULL)
+ * with candidate lists large enough for every score, zeroes the counters and fills sinks[num_levels]
+ * (host array); after the convolutions have run on the same stream (or on streams ordered after it),
+ * odtk_decode_fused_finish selects the top_n per level and decodes the boxes exactly like
+ * odtk_decode_levels.  levels[].scores is ignored (may be NULL); deltas are read by _finish only. */
+typedef struct {
+  int *counts;          /* device [B]: candidates appended per image                 */
+  uint32_t *hist;       /* device [B, hist_bins]: score-key histogram per image      */
+  void *cand;           /* device [B, cap] (uint32 key, uint32 flat index) pairs     */
+  long long cap;
+  uint32_t key_thresh;
+  int shift, hist_bins;
+  float thresh;         /* a score is a candidate iff score > thresh                 */
+} odtk_cand_sink_t;
+
+long long odtk_decode_fused_begin(int batch, int num_levels, const odtk_level_t *levels, size_t num_anchors,
+                                  size_t num_classes, float score_thresh, int top_n, odtk_cand_sink_t *sinks,
+                                  void *workspace, size_t workspace_size, odtk_stream_t stream);
+long long odtk_decode_fused_finish(int batch, int num_levels, const odtk_level_t *levels, size_t num_anchors,
+                                   size_t num_classes, size_t num_anchor_floats, float score_thresh, int top_n,
+                                   int nbox, void *const *outputs, size_t out_stride, size_t out_offset,
+                                   void *workspace, size_t workspace_size, odtk_stream_t stream);
+
 /* ---- nms ----------------------------------------------------------------------
  * Replaces odtk::cuda::nms (csrc/cuda/nms.h:28-31, nms.cu:82-160) and
  * odtk::cuda::nms_rotate (nms_iou.h:28-31, nms_iou.cu:260-322).
@@ -129,6 +155,7 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
 #define ODTK_OUT_NHWC_F16 0          /* y: [N, H, W, ldy] fp16                          */
 #define ODTK_OUT_NCHW_F32 1          /* y: [N, Cout, H, W] fp32 (box head output)       */
 #define ODTK_OUT_NCHW_F32_SIGMOID 2  /* same, sigmoid applied (odtk/model.py:140)       */
+#define ODTK_OUT_CANDIDATES 3        /* sigmoid applied, scores > thresh appended to `sink` (y unused) */
 typedef struct {
   const void *x;        /* NHWC fp16 [n, h, width, cin]                                 */
   const void *w;        /* fp16 [cout, ksize*ksize*cin]                                 */
@@ -140,6 +167,7 @@ typedef struct {
   int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2) on even h, width; y is [n, h/2, width/2, ...] */
   const void *bias_op;  /* optional: bias packed by odtk_conv_pack_bias ([cout, 64] fp16).  When given, the
                            bias is added by ONE extra K block on the tensor core instead of in the epilogue */
+  const odtk_cand_sink_t *sink; /* out_mode ODTK_OUT_CANDIDATES: where the candidates go (host struct)       */
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
 /* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */

@@ -97,6 +97,56 @@ def decode_levels(cls_heads, box_heads, anchors, scales, score_thresh, top_n, ro
     return [scores, boxes, classes]
 
 
+class FusedDecode:
+    """The two halves of odtk_decode_fused_begin / _finish (include/odtk_b200.h) for one fixed batch and
+    pyramid geometry.  `begin()` zeroes the counters and returns one CandSink per level, to be handed to the
+    class head's last convolution (engine.conv2d(..., out_mode=OUT_CANDIDATES, sink=...)); `finish(box_heads)`
+    returns what decode_levels would have returned for the dense score maps.  The workspace is owned by the
+    object, so its addresses are stable across CUDA-graph replays."""
+
+    def __init__(self, batch, sizes, num_anchors, num_classes, anchors, scales, score_thresh, top_n, rotated, device):
+        self.batch, self.nl, self.nbox = int(batch), len(sizes), 6 if rotated else 4
+        self.num_anchors, self.num_classes = int(num_anchors), int(num_classes)
+        self.thresh, self.top_n, self.device = float(score_thresh), int(top_n), device
+        self.na_floats = len(anchors[0]) if anchors and anchors[0] is not None else 0
+        self.levels = (_lib.Level * self.nl)()
+        self._keep = []
+        for i, (h, w) in enumerate(sizes):
+            anc = (ctypes.c_float * max(1, self.na_floats))(*[float(a) for a in (anchors[i] if self.na_floats else [])])
+            self._keep.append(anc)
+            self.levels[i].scores, self.levels[i].deltas = None, None
+            self.levels[i].height, self.levels[i].width, self.levels[i].scale = int(h), int(w), int(scales[i])
+            self.levels[i].anchors = ctypes.cast(anc, ctypes.POINTER(ctypes.c_float))
+        self.sinks = (_lib.CandSink * self.nl)()
+        L = _lib.lib()
+        self.size = _lib.check(L.odtk_decode_fused_begin(*self._begin_args(), None, 0, None), "decode_fused (workspace query)")
+        self.scratch = _workspace(self.size, device)
+
+    def _begin_args(self):
+        return (self.batch, self.nl, ctypes.cast(self.levels, ctypes.c_void_p), self.num_anchors, self.num_classes,
+                self.thresh, self.top_n, ctypes.cast(self.sinks, ctypes.c_void_p))
+
+    def begin(self):
+        _lib.check(_lib.lib().odtk_decode_fused_begin(*self._begin_args(), ctypes.c_void_p(self.scratch.data_ptr()),
+                                                      self.size, _stream()), "decode_fused_begin")
+        return self.sinks
+
+    def finish(self, box_heads):
+        for i, b in enumerate(box_heads):
+            _check_input(b, "box_head")
+            self.levels[i].deltas = b.data_ptr()
+        n = self.nl * self.top_n
+        scores = torch.empty((self.batch, n), dtype=torch.float32, device=self.device)
+        boxes = torch.empty((self.batch, n, self.nbox), dtype=torch.float32, device=self.device)
+        classes = torch.empty((self.batch, n), dtype=torch.float32, device=self.device)
+        outputs = _lib.ptr_array([scores.data_ptr(), boxes.data_ptr(), classes.data_ptr()])
+        _lib.check(_lib.lib().odtk_decode_fused_finish(
+            self.batch, self.nl, ctypes.cast(self.levels, ctypes.c_void_p), self.num_anchors, self.num_classes,
+            self.na_floats, self.thresh, self.top_n, self.nbox, outputs, n, 0,
+            ctypes.c_void_p(self.scratch.data_ptr()), self.size, _stream()), "decode_fused_finish")
+        return [scores, boxes, classes]
+
+
 def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, return_index=False,
         fixed_angle=False):
     """odtk._C.nms (csrc/extensions.cpp:117-158).

@@ -31,6 +31,13 @@ SIGNATURES = {
                                                ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
                                                ctypes.c_int, _c_vpp, ctypes.c_size_t, ctypes.c_size_t,
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_decode_fused_begin": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                    ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_decode_fused_finish": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                                     ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
+                                                     ctypes.c_int, _c_vpp, ctypes.c_size_t, ctypes.c_size_t,
+                                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_nms": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_nms_rotate": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int,
@@ -61,6 +68,13 @@ class Level(ctypes.Structure):
     """odtk_level_t (include/odtk_b200.h)."""
     _fields_ = [("scores", ctypes.c_void_p), ("deltas", ctypes.c_void_p), ("height", ctypes.c_size_t),
                 ("width", ctypes.c_size_t), ("scale", ctypes.c_size_t), ("anchors", _c_f32p)]
+
+
+class CandSink(ctypes.Structure):
+    """odtk_cand_sink_t (include/odtk_b200.h)."""
+    _fields_ = [("counts", ctypes.c_void_p), ("hist", ctypes.c_void_p), ("cand", ctypes.c_void_p),
+                ("cap", ctypes.c_longlong), ("key_thresh", ctypes.c_uint32), ("shift", ctypes.c_int),
+                ("hist_bins", ctypes.c_int), ("thresh", ctypes.c_float)]
 
 
 _LIB = None

@@ -25,6 +25,7 @@
 // Strided and 7x7 convolutions are lowered by layers.cu to one of the two forms.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -635,6 +636,70 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           w = rem - h * p.W;
         }
         const long long cs = hw;
+        if (p.out_mode == ODTK_OUT_CANDIDATES) {
+          // class-head final layer: only the scores above the threshold leave the SM, appended to the decode
+          // workspace as (key, flat NCHW index) pairs + the key histogram, exactly what decode.cu's
+          // score_filter_kernel would have produced from the dense map
+          const int pix = h * p.W + w;
+          for (int c = sg; c < nchunks; c += kEpiWarps / 4) {
+            uint32_t v[16];
+            tc_ld16(taddr + (uint32_t)(c * 16), v);
+            tc_ld_wait();
+            const int col0 = n0 + c * 16;
+            const int ncol = min(16, p.Cout - col0);
+            unsigned pass = 0;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                if (j < ncol) {
+                  float x = __uint_as_float(v[j]) + ((p.bias && !p.bias_mma) ? __ldg(p.bias + col0 + j) : 0.0f);
+                  if (p.relu) x = fmaxf(x, 0.0f);
+                  v[j] = __float_as_uint(x);
+                  if (x > p.cand_pre) pass |= 1u << j;     // cheap pre-test; the exact test follows
+                }
+              }
+            }
+            if (!__any_sync(0xffffffffu, pass != 0)) continue;   // almost every chunk: nothing to do
+            unsigned hit = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if ((pass >> j) & 1u) {
+                const float sc = sigmoidf_accurate(__uint_as_float(v[j]));
+                v[j] = __float_as_uint(sc);
+                if (sc > p.cand_thresh) hit |= 1u << j;
+              }
+            const int cnt = __popc(hit);
+            int base;
+            if (p.mode != 0) {   // the whole tile lies in one image: one atomic per warp
+              int incl = cnt;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+              }
+              const int total = __shfl_sync(0xffffffffu, incl, 31);
+              if (total == 0) continue;
+              int b0 = 0;
+              if (lane == 0) b0 = atomicAdd(p.cand_counts + img, total);
+              base = __shfl_sync(0xffffffffu, b0, 0) + incl - cnt;
+            } else {
+              base = cnt ? atomicAdd(p.cand_counts + img, cnt) : 0;
+            }
+            if (cnt) {
+              uint2 *dst = p.cand + (long long)img * p.cand_cap;
+              unsigned *hist = p.cand_hist + (long long)img * p.cand_hist_bins;
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if ((hit >> j) & 1u) {
+                  const uint32_t key = odtk_float_key(__uint_as_float(v[j]));
+                  if ((long long)base < p.cand_cap) dst[base] = make_uint2(key, (uint32_t)((col0 + j) * hw + pix));
+                  base++;
+                  const uint32_t dd = (key - p.cand_key_thresh) >> p.cand_shift;
+                  atomicAdd(hist + (dd < (uint32_t)(p.cand_hist_bins - 1) ? dd : (uint32_t)(p.cand_hist_bins - 1)), 1u);
+                }
+            }
+          }
+        } else
         for (int c = sg; c < nchunks; c += kEpiWarps / 4) {
           uint32_t v[16];
           tc_ld16(taddr + (uint32_t)(c * 16), v);
@@ -803,15 +868,16 @@ const void *ones_operand(cudaStream_t stream) {
 }  // namespace
 
 extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
-  if (!d || !d->x || !d->w || !d->y) return ODTK_E_INVALID;
+  if (!d || !d->x || !d->w) return ODTK_E_INVALID;
+  if (d->out_mode == ODTK_OUT_CANDIDATES ? !d->sink : !d->y) return ODTK_E_INVALID;
   if (d->n <= 0 || d->h <= 0 || d->width <= 0 || d->cin <= 0 || d->cout <= 0) return ODTK_E_INVALID;
   if (d->ksize != 1 && d->ksize != 3) return ODTK_E_UNSUPPORTED;
   if (d->cin % 64 != 0) return ODTK_E_UNSUPPORTED;  // 64-channel K blocks (128-byte swizzle rows)
-  if (d->out_mode < 0 || d->out_mode > 2) return ODTK_E_INVALID;
+  if (d->out_mode < 0 || d->out_mode > 3) return ODTK_E_INVALID;
   if (d->out_mode == ODTK_OUT_NHWC_F16 && (d->cout % 16)) return ODTK_E_UNSUPPORTED;
   if (d->out_mode != ODTK_OUT_NHWC_F16 && (d->residual || d->upsample)) return ODTK_E_UNSUPPORTED;
   if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
-  if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y) & 15) return ODTK_E_INVALID;
+  if (((uintptr_t)d->x | (uintptr_t)d->w | (d->out_mode == ODTK_OUT_CANDIDATES ? 0 : (uintptr_t)d->y)) & 15) return ODTK_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!g_num_sms) {
     int dev = 0;
@@ -846,6 +912,16 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   p.ldy = d->ldy > 0 ? d->ldy : d->cout;
   p.ldr = d->ldr > 0 ? d->ldr : d->cout;
   p.up_h = d->h / 2; p.up_w = d->width / 2;
+  if (p.out_mode == ODTK_OUT_CANDIDATES) {
+    const odtk_cand_sink_t *k = d->sink;
+    if (!k->counts || !k->hist || !k->cand || k->hist_bins <= 0) return ODTK_E_INVALID;
+    if ((long long)d->cout * d->h * d->width >= (1ll << 32)) return ODTK_E_UNSUPPORTED;
+    p.cand_counts = k->counts; p.cand_hist = k->hist; p.cand = (uint2 *)k->cand; p.cand_cap = k->cap;
+    p.cand_key_thresh = k->key_thresh; p.cand_shift = k->shift; p.cand_hist_bins = k->hist_bins;
+    p.cand_thresh = k->thresh;
+    // sigmoid(x) > thresh implies x > logit(thresh) - margin (the SFU sigmoid is accurate to 1e-6 relative)
+    p.cand_pre = (k->thresh > 1e-4f && k->thresh < 0.999f) ? logf(k->thresh / (1.0f - k->thresh)) - 0.05f : -INFINITY;
+  }
   if (p.out_mode == ODTK_OUT_NHWC_F16 && (p.ldy % 8)) return ODTK_E_INVALID;
   if (d->upsample && ((d->h & 1) || (d->width & 1))) return ODTK_E_INVALID;
   if (d->upsample && BN <= 128) return ODTK_E_UNSUPPORTED;  // the upsample-add epilogue is built for 256-wide tiles

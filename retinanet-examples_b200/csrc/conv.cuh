@@ -21,4 +21,12 @@ struct ConvParams {
   int bias_mma;         // the bias is added by one extra K block on the tensor core (A = ones, B = bias hi/lo)
   int tma_store;        // epilogue hands 32x64 slabs to cp.async.bulk.tensor stores (mode 0, BN > 128)
   int nstages;          // pipeline stages that fit: (16 KB + BN*128 B) each
+  // out_mode ODTK_OUT_CANDIDATES: the decode workspace of this pyramid level (decode.cu)
+  int *cand_counts;          // [N]
+  unsigned *cand_hist;       // [N, cand_hist_bins]
+  uint2 *cand;               // [N, cand_cap]
+  long long cand_cap;
+  unsigned cand_key_thresh;
+  int cand_shift, cand_hist_bins;
+  float cand_thresh, cand_pre;   // candidate iff sigmoid(x) > thresh; x <= cand_pre can never pass
 };

@@ -470,11 +470,15 @@ int choose_shift(uint32_t key_thresh) {
 
 }  // namespace
 
-extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_level_t *levels,
-                                        size_t num_anchors, size_t num_classes, size_t num_anchor_floats,
-                                        float score_thresh, int top_n, int nbox, void *const *outputs,
-                                        size_t out_stride, size_t out_offset, void *workspace,
-                                        size_t workspace_size, odtk_stream_t stream_) {
+// mode 0: filter + gather + select (the drop-in path).  mode 1 ("begin"): lay out a workspace whose candidate
+// lists can hold EVERY score (no overflow possible), zero the counters and describe the per-level sinks -- the
+// class-head convolution's epilogue appends the candidates itself (conv.cu, ODTK_OUT_CANDIDATES).
+// mode 2 ("finish"): gather + select + decode on those lists.
+static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch, int num_levels,
+                                    const odtk_level_t *levels, size_t num_anchors, size_t num_classes,
+                                    size_t num_anchor_floats, float score_thresh, int top_n, int nbox,
+                                    void *const *outputs, size_t out_stride, size_t out_offset, void *workspace,
+                                    size_t workspace_size, odtk_stream_t stream_) {
   if (batch <= 0 || num_levels <= 0 || !levels || num_anchors == 0 || num_classes == 0 || top_n <= 0)
     return ODTK_E_INVALID;
   if (nbox != 4 && nbox != 6) return ODTK_E_INVALID;
@@ -490,7 +494,7 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
     long long n = (long long)num_anchors * num_classes * levels[l].height * levels[l].width;
     if (n >= (1ll << 31)) return ODTK_E_UNSUPPORTED;  // flat index is int32 (decode.cu:122)
     p.lv[l].n = n;
-    p.lv[l].cap = level_cap(n, top_n);
+    p.lv[l].cap = (mode == 0) ? level_cap(n, top_n) : (n > top_n ? n : top_n);
     p.lv[l].cand_off = cand_entries;
     cand_entries += p.lv[l].cap * batch;
     total_n += n;
@@ -505,8 +509,10 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
   ws.total = ws.cand_off + odtk_align_up((size_t)cand_entries * sizeof(uint2));
   if (!workspace || !workspace_size) return (long long)ws.total;
   if (workspace_size < ws.total) return ODTK_E_WORKSPACE;
-  if (!outputs || !outputs[0] || !outputs[1] || !outputs[2]) return ODTK_E_INVALID;
-  if (out_stride < out_offset + (size_t)top_n * num_levels) return ODTK_E_INVALID;
+  if (mode != 1) {
+    if (!outputs || !outputs[0] || !outputs[1] || !outputs[2]) return ODTK_E_INVALID;
+    if (out_stride < out_offset + (size_t)top_n * num_levels) return ODTK_E_INVALID;
+  }
   cudaStream_t stream = (cudaStream_t)stream_;
   char *base = (char *)workspace;
 
@@ -522,7 +528,7 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
   int blk = 0;
   for (int l = 0; l < num_levels; l++) {
     LevelDesc &L = p.lv[l];
-    if (!levels[l].scores || !levels[l].deltas) return ODTK_E_INVALID;
+    if ((mode == 0 && !levels[l].scores) || (mode != 1 && !levels[l].deltas)) return ODTK_E_INVALID;
     if (num_anchor_floats && !levels[l].anchors) return ODTK_E_INVALID;
     L.scores = (const float *)levels[l].scores;
     L.deltas = (const float *)levels[l].deltas;
@@ -557,13 +563,27 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
   p.hist = (uint32_t *)(base + ws.hist_off);
   p.sel = (unsigned long long *)(base + ws.sel_off);
   p.cand = (uint2 *)(base + ws.cand_off);
-  p.out_scores = (float *)outputs[0];
-  p.out_boxes = (float *)outputs[1];
-  p.out_classes = (float *)outputs[2];
+  p.out_scores = mode != 1 ? (float *)outputs[0] : nullptr;
+  p.out_boxes = mode != 1 ? (float *)outputs[1] : nullptr;
+  p.out_classes = mode != 1 ? (float *)outputs[2] : nullptr;
   p.out_stride = (long long)out_stride;
 
-  if (cudaMemsetAsync(base, 0, ws.zero_bytes, stream) != cudaSuccess) return ODTK_E_CUDA;
-  {
+  if (mode != 2 && cudaMemsetAsync(base, 0, ws.zero_bytes, stream) != cudaSuccess) return ODTK_E_CUDA;
+  if (mode == 1) {
+    if (!sinks) return ODTK_E_INVALID;
+    for (int l = 0; l < num_levels; l++) {
+      sinks[l].counts = p.counts + (size_t)l * batch;
+      sinks[l].hist = p.hist + (size_t)l * batch * kHistBins;
+      sinks[l].cand = p.cand + p.lv[l].cand_off;
+      sinks[l].cap = p.lv[l].cap;
+      sinks[l].key_thresh = p.key_thresh;
+      sinks[l].shift = p.shift;
+      sinks[l].thresh = score_thresh;
+      sinks[l].hist_bins = kHistBins;
+    }
+    return ODTK_OK;
+  }
+  if (mode == 0) {
     OdtkProfScope prof(ODTK_PROF_FILTER, stream);
     score_filter_kernel<<<blk, kFilterThreads, 0, stream>>>(p);
   }
@@ -574,6 +594,31 @@ extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_le
     else           select_decode_kernel<6><<<slots, 1024, 0, stream>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" long long odtk_decode_levels(int batch, int num_levels, const odtk_level_t *levels,
+                                        size_t num_anchors, size_t num_classes, size_t num_anchor_floats,
+                                        float score_thresh, int top_n, int nbox, void *const *outputs,
+                                        size_t out_stride, size_t out_offset, void *workspace,
+                                        size_t workspace_size, odtk_stream_t stream) {
+  return decode_levels_impl(0, nullptr, batch, num_levels, levels, num_anchors, num_classes, num_anchor_floats,
+                            score_thresh, top_n, nbox, outputs, out_stride, out_offset, workspace, workspace_size, stream);
+}
+
+extern "C" long long odtk_decode_fused_begin(int batch, int num_levels, const odtk_level_t *levels, size_t num_anchors,
+                                             size_t num_classes, float score_thresh, int top_n, odtk_cand_sink_t *sinks,
+                                             void *workspace, size_t workspace_size, odtk_stream_t stream) {
+  return decode_levels_impl(1, sinks, batch, num_levels, levels, num_anchors, num_classes, 0, score_thresh, top_n, 4,
+                            nullptr, 0, 0, workspace, workspace_size, stream);
+}
+
+extern "C" long long odtk_decode_fused_finish(int batch, int num_levels, const odtk_level_t *levels, size_t num_anchors,
+                                              size_t num_classes, size_t num_anchor_floats, float score_thresh,
+                                              int top_n, int nbox, void *const *outputs, size_t out_stride,
+                                              size_t out_offset, void *workspace, size_t workspace_size,
+                                              odtk_stream_t stream) {
+  return decode_levels_impl(2, nullptr, batch, num_levels, levels, num_anchors, num_classes, num_anchor_floats,
+                            score_thresh, top_n, nbox, outputs, out_stride, out_offset, workspace, workspace_size, stream);
 }
 
 extern "C" long long odtk_decode_ex(int batch, const void *const *inputs, void *const *outputs,

@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 
-OUT_NHWC_F16, OUT_NCHW_F32, OUT_NCHW_F32_SIGMOID = 0, 1, 2
+OUT_NHWC_F16, OUT_NCHW_F32, OUT_NCHW_F32_SIGMOID, OUT_CANDIDATES = 0, 1, 2, 3
 
 # host-side accounting of what was launched (bench.py reads it): kernels launched by this
 # module and algorithmic convolution FLOPs (2 * pixels * Cout * taps * Cin, unpadded)
@@ -19,7 +19,8 @@ class ConvDesc(ctypes.Structure):
                 ("residual", ctypes.c_void_p), ("upsample", ctypes.c_void_p), ("y", ctypes.c_void_p),
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
                 ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
-                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int), ("bias_op", ctypes.c_void_p)]
+                ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int), ("bias_op", ctypes.c_void_p),
+                ("sink", ctypes.c_void_p)]
 
 
 def _stream():
@@ -52,19 +53,22 @@ def pack_bias(bias):
 
 
 def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None,
-           stride=1, bias_op=None):
+           stride=1, bias_op=None, sink=None):
     """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
     Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
     assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
     n, h, wd, cin = x.shape
     oh, ow = (h // 2, wd // 2) if stride == 2 else (h, wd)
-    if out is None:
+    if out_mode == OUT_CANDIDATES:
+        assert sink is not None
+    elif out is None:
         if out_mode == OUT_NHWC_F16:
             out = torch.empty((n, oh, ow, cout), dtype=torch.float16, device=x.device)
         else:
             out = torch.empty((n, cout, oh, ow), dtype=torch.float32, device=x.device)
     d = ConvDesc()
-    d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), (out.data_ptr() if out is not None else None)
+    d.sink = ctypes.addressof(sink) if sink is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.upsample = upsample.data_ptr() if upsample is not None else None

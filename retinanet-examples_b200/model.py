@@ -13,6 +13,7 @@ odtk/backbones/resnet.py:24-39, torchvision BasicBlock/Bottleneck):
   of each head writes fp32 NCHW (sigmoid fused for the class head) which feeds the all-levels
   decode (3 launches) and the batched NMS (1 launch)."""
 import math
+import os
 
 import numpy as np
 import torch
@@ -102,14 +103,17 @@ class _Conv:
         self.b = bias.float().contiguous().to(device) if bias is not None else None
         self.bop = engine.pack_bias(self.b) if self.b is not None else None     # bias as a tensor-core K block
 
-    def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False):
+    def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False,
+                 sink=None):
         oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
         engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin
         if self.stem and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and residual is None and upsample is None:
             return engine.stem_conv(x, self.w_stem, self.b, self.cout, relu)
         if self.direct:
             assert not in_relu
-            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode, bias_op=self.bop)
+            return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode,
+                                 bias_op=self.bop, sink=sink)
+        assert sink is None
         if (self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and not in_relu and upsample is None
                 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0):
             # even-sized stride-2 convolution: strided TMA view, no gather pre-pass
@@ -150,6 +154,8 @@ class Model:
         self._packed = None
         self.device = None
         self.parallel_heads = True
+        self.fused_candidates = os.environ.get("ODTK_FUSED_CANDIDATES", "1") != "0"
+        self._fused = {}
         self._head_streams = None
 
     def __repr__(self):
@@ -256,7 +262,7 @@ class Model:
         p7 = P["pyramid7"](p6, in_relu=True)
         return [P["smooth3"](p3), P["smooth4"](p4), P["smooth5"](p5), p6, p7]
 
-    def _heads(self, features, sigmoid=True):
+    def _heads(self, features, sigmoid=True, sinks=None):
         """Class / box heads on the five levels (odtk/model.py:134-135).  The ten conv chains are
         independent, so each runs on its own CUDA stream (fork after the FPN, join before decode): the
         small levels' launches (P5-P7 use 1-32 CTAs) overlap each other and the tail of the big
@@ -266,14 +272,16 @@ class Model:
         cls_heads, box_heads = [None] * nl, [None] * nl
         cls_mode = engine.OUT_NCHW_F32_SIGMOID if sigmoid else engine.OUT_NCHW_F32
 
-        def chain(head, t, final_mode):
+        def chain(head, t, final_mode, sink=None):
             for conv in P[head][:-1]:
                 t = conv(t, relu=True)
+            if sink is not None:      # class scores go straight to the decode workspace (no dense map)
+                return P[head][-1](t, out_mode=engine.OUT_CANDIDATES, sink=sink)
             return P[head][-1](t, out_mode=final_mode)
 
         if not self.parallel_heads:
             for i, t in enumerate(features):
-                cls_heads[i] = chain("cls_head", t, cls_mode)
+                cls_heads[i] = chain("cls_head", t, cls_mode, sinks[i] if sinks is not None else None)
                 box_heads[i] = chain("box_head", t, engine.OUT_NCHW_F32)
             return cls_heads, box_heads
         main = torch.cuda.current_stream()
@@ -284,13 +292,14 @@ class Model:
         joins = []
         for i, t in enumerate(features):
             for j, (head, mode) in enumerate((("cls_head", cls_mode), ("box_head", engine.OUT_NCHW_F32))):
+                sink = sinks[i] if (sinks is not None and j == 0) else None
                 if i == 0 and j == 0:          # the biggest chain stays on the main stream
-                    cls_heads[0] = chain(head, t, mode)
+                    cls_heads[0] = chain(head, t, mode, sink)
                     continue
                 st = self._head_streams[2 * i + j]
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    out = chain(head, t, mode)
+                    out = chain(head, t, mode, sink)
                     ev = torch.cuda.Event()
                     ev.record(st)
                 joins.append(ev)
@@ -325,7 +334,49 @@ class Model:
             raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
         return self._heads(self._features(self._to_nhwc_half(x)), sigmoid)
 
+    def _level_anchors(self, widths, width):
+        strides, anchors = [], []
+        for w in widths:
+            stride = width // w                            # width only (odtk/model.py:155)
+            if stride not in self.anchors:
+                self.anchors[stride] = (box.generate_anchors_rotated(stride, self.ratios, self.scales, self.angles)
+                                        if self.rotated_bbox else box.generate_anchors(stride, self.ratios, self.scales))
+            a = self.anchors[stride][0] if self.rotated_bbox else self.anchors[stride]
+            strides.append(stride)
+            anchors.append(a.reshape(-1).tolist())
+        return strides, anchors
+
+    def _forward_fused(self, x):
+        """Inference branch with the class head's last convolution appending its above-threshold scores
+        directly to the decode workspace (odtk_decode_fused_begin/_finish): the dense [B, A*C, H, W] score maps
+        of odtk/model.py:140 are never written or re-read.  Same detections as the dense route."""
+        if self._packed is None:
+            raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
+        if x.dtype == torch.uint8:
+            xp, hs, width = engine.preprocess_u8(x, self.stride)
+            stem = self._packed["stem"]
+            engine.STATS["conv_flops"] += 2 * x.shape[0] * (hs // 2) * (width // 2) * stem.cout * 49 * 3
+            features = self._features(engine.stem_conv_padded(xp, hs, width, stem.w_stem, stem.b, stem.cout, relu=True),
+                                      stem_done=True)
+        else:
+            width = x.shape[-1]
+            features = self._features(self._to_nhwc_half(x))
+        sizes = tuple((f.shape[1], f.shape[2]) for f in features)
+        batch = features[0].shape[0]
+        key = (batch, sizes, width, self.threshold, self.top_n, self.rotated_bbox)
+        fd = self._fused.get(key)
+        if fd is None:
+            strides, anchors = self._level_anchors([s[1] for s in sizes], width)
+            num_anchors = len(anchors[0]) // 4
+            fd = self._fused[key] = _C.FusedDecode(batch, sizes, num_anchors, self.classes, anchors, strides,
+                                                   self.threshold, self.top_n, self.rotated_bbox, features[0].device)
+        sinks = fd.begin()
+        _, box_heads = self._heads(features, True, sinks)
+        return tuple(_C.nms(*fd.finish(box_heads), self.nms, self.detections, self.rotated_bbox))
+
     def forward(self, x, rotated_bbox=None):
+        if self.fused_candidates and not self.exporting:
+            return self._forward_fused(x)
         if x.dtype == torch.uint8:                       # raw HWC images: fused input side
             (cls_heads, box_heads), (_, width) = self.forward_heads_u8(x)
         else:
@@ -334,15 +385,7 @@ class Model:
         if self.exporting:
             self.strides = [width // c.shape[-1] for c in cls_heads]
             return cls_heads, box_heads
-        strides, anchors = [], []
-        for c in cls_heads:
-            stride = width // c.shape[-1]                  # width only (odtk/model.py:155)
-            if stride not in self.anchors:
-                self.anchors[stride] = (box.generate_anchors_rotated(stride, self.ratios, self.scales, self.angles)
-                                        if self.rotated_bbox else box.generate_anchors(stride, self.ratios, self.scales))
-            a = self.anchors[stride][0] if self.rotated_bbox else self.anchors[stride]
-            strides.append(stride)
-            anchors.append(a.reshape(-1).tolist())
+        strides, anchors = self._level_anchors([c.shape[-1] for c in cls_heads], width)
         decoded = _C.decode_levels(cls_heads, box_heads, anchors, strides, self.threshold, self.top_n, self.rotated_bbox)
         return tuple(_C.nms(*decoded, self.nms, self.detections, self.rotated_bbox))
 

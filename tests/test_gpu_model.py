@@ -119,6 +119,33 @@ def test_parallel_head_streams_equal_sequential():
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("threshold,top_n", [(0.05, 1000), (0.0, 300), (0.3, 50), (0.02, 4096)])
+def test_fused_candidate_epilogue_equals_dense_route(threshold, top_n):
+    """The class head's last convolution appending candidates itself (ODTK_OUT_CANDIDATES +
+    odtk_decode_fused_*) must give bit-identical detections to dense score maps + odtk_decode_levels;
+    threshold 0 makes EVERY score a candidate (the worst case for the epilogue's atomics)."""
+    backbone, classes = "ResNet18FPN", 7
+    sd = _spread_head(make_state_dict(backbone, classes, 9, False, 21), std=0.08, prior=0.03)
+    m = Model(backbone, classes=classes, config={"threshold": threshold, "top_n": top_n, "detections": 200})
+    m.load_state_dict(sd).cuda()
+    x = torch.randn((3, 3, 256, 320), generator=torch.Generator().manual_seed(8)).to(DEV)
+    m.fused_candidates = False
+    dense = [t.clone() for t in m(x)]
+    assert (dense[0] > 0).sum() > 20
+    m.fused_candidates = True
+    for _ in range(2):
+        fused = m(x)
+        for a, b in zip(fused, dense):
+            assert torch.equal(a, b)
+    # raw uint8 input takes the same fused route
+    img = torch.randint(0, 256, (2, 200, 300, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9)).to(DEV)
+    m.fused_candidates = False
+    dense = [t.clone() for t in m(img)]
+    m.fused_candidates = True
+    for a, b in zip(m(img), dense):
+        assert torch.equal(a, b)
+
+
 def test_uint8_input_side_fused(golden_dir):
     """uint8 HWC images -> normalise + stride pad (odtk/data.py:113-123) fused into the stem's input buffer."""
     from retinanet_examples_b200 import engine
