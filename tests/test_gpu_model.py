@@ -119,16 +119,19 @@ def test_parallel_head_streams_equal_sequential():
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("threshold,top_n", [(0.05, 1000), (0.0, 300), (0.3, 50), (0.02, 4096)])
+@pytest.mark.parametrize("threshold,top_n", [(0.05, 1000), (0.0, 300), (None, 50), (0.02, 4096)])
 def test_fused_candidate_epilogue_equals_dense_route(threshold, top_n):
     """The class head's last convolution appending candidates itself (ODTK_OUT_CANDIDATES +
     odtk_decode_fused_*) must give bit-identical detections to dense score maps + odtk_decode_levels;
     threshold 0 makes EVERY score a candidate (the worst case for the epilogue's atomics)."""
     backbone, classes = "ResNet18FPN", 7
     sd = _spread_head(make_state_dict(backbone, classes, 9, False, 21), std=0.08, prior=0.03)
-    m = Model(backbone, classes=classes, config={"threshold": threshold, "top_n": top_n, "detections": 200})
+    m = Model(backbone, classes=classes, config={"threshold": threshold or 0.05, "top_n": top_n, "detections": 200})
     m.load_state_dict(sd).cuda()
     x = torch.randn((3, 3, 256, 320), generator=torch.Generator().manual_seed(8)).to(DEV)
+    if threshold is None:      # a high threshold that still leaves ~3000 candidates: few per level, count < top_n
+        allscores = torch.cat([c.flatten() for c in m.forward_heads(x)[0]])
+        m.threshold = float(allscores.topk(3000).values[-1])
     m.fused_candidates = False
     dense = [t.clone() for t in m(x)]
     assert (dense[0] > 0).sum() > 20
