@@ -134,8 +134,14 @@ class FullWorkload:
         self.out = None
         self.world_gather = None
         engine.STATS["launches"] = engine.STATS["conv_flops"] = 0
+        engine.STATS["trace"] = []
+        self.model.parallel_heads = False         # trace in the order step_profile() launches
         self.model.forward(self.dev_x)            # eager pass: counts launches / algorithmic FLOPs
+        self.model.parallel_heads = True
         torch.cuda.synchronize()
+        self.trace, engine.STATS["trace"] = engine.STATS["trace"], None
+        if os.environ.get("ODTK_BENCH_TRACE"):
+            json.dump(self.trace, open(os.environ["ODTK_BENCH_TRACE"], "w"))
         # + decode (filter, gather, select: the filter launch disappears when the class head's last
         #   convolution appends the candidates itself) + nms (1); memsets are not counted
         self.launches_per_step = engine.STATS["launches"] + (3 if self.model.fused_candidates else 4)
@@ -211,6 +217,16 @@ class FullWorkload:
         flops = float(self.flops_per_step) * steps
         achieved = flops / (ms * 1e-3) / 1e12
         peak = peaks["tensor_sustained"] or peaks["tensor"]
+        # layer-by-layer speed of light: every launch at max(FLOPs / tensor peak, algorithmic bytes / HBM peak)
+        t_tc = [l["flops"] / (peak * 1e12) for l in self.trace]
+        t_hbm = [l["bytes"] / (peaks["hbm"] * 1e9) for l in self.trace]
+        ideal = [max(a, b) for a, b in zip(t_tc, t_hbm)]
+        self.layerwise = {"ideal_ms_per_step": round(sum(ideal) * 1e3, 3),
+                          "tensor_bound_ms": round(sum(i for i, a, b in zip(ideal, t_tc, t_hbm) if a >= b) * 1e3, 3),
+                          "hbm_bound_ms": round(sum(i for i, a, b in zip(ideal, t_tc, t_hbm) if a < b) * 1e3, 3),
+                          "algorithmic_bytes_per_step": int(sum(l["bytes"] for l in self.trace)),
+                          "note": "sum over the step's launches of max(FLOPs/tensor peak, operand+output bytes/HBM peak): "
+                                  "the bound of layer-by-layer execution; frac_of_step = ideal / measured ms_per_step"}
         return {"kernel": "conv_gemm_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum summed over the 111 conv launches of ONE step
@@ -429,6 +445,9 @@ def main():
         if roof is not None and "conv_share_of_step" in roof:
             cms, _ = _prof_get(lib, 3)
             roof["conv_share_of_step"] = round(cms / ms_prof, 4)
+        if roof is not None and getattr(wl, "layerwise", None):
+            wl.layerwise["frac_of_step"] = round(wl.layerwise["ideal_ms_per_step"] / (ms / args.steps), 4)
+            roof["layerwise"] = wl.layerwise
         ms_e2e = None
         if not args.no_e2e:
             for _ in range(2):

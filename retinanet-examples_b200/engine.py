@@ -10,7 +10,16 @@ OUT_NHWC_F16, OUT_NCHW_F32, OUT_NCHW_F32_SIGMOID, OUT_CANDIDATES = 0, 1, 2, 3
 
 # host-side accounting of what was launched (bench.py reads it): kernels launched by this
 # module and algorithmic convolution FLOPs (2 * pixels * Cout * taps * Cin, unpadded)
-STATS = {"launches": 0, "conv_flops": 0}
+STATS = {"launches": 0, "conv_flops": 0, "trace": None}
+
+
+def _trace(kind, flops, nbytes, **shape):
+    """When STATS["trace"] is a list, every kernel launch appends (kind, algorithmic FLOPs, algorithmic HBM bytes =
+    every operand read once + the output written once, shape): bench.py's layer-wise roofline and the per-launch ncu
+    tables in profiles/ are keyed on this order."""
+    if STATS["trace"] is not None:
+        STATS["trace"].append(dict(kind=kind, flops=int(flops), bytes=int(nbytes), **shape))
+
 
 
 class ConvDesc(ctypes.Structure):
@@ -77,6 +86,14 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     d.bias_op = bias_op.data_ptr() if bias_op is not None else None
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
     STATS["launches"] += 1
+    if STATS["trace"] is not None:
+        px = n * oh * ow
+        obytes = 0 if out_mode == OUT_CANDIDATES else px * cout * (2 if out_mode == OUT_NHWC_F16 else 4)
+        _trace("conv%dx%d" % (ksize, ksize), 2 * px * cout * ksize * ksize * cin,
+               (px * cin * 2 if (ksize == 1 and stride == 2) else x.numel() * 2) + w.numel() * 2 + obytes + (px * cout * 2 if residual is not None else 0)
+               + (px * cout // 2 if upsample is not None else 0),
+               n=n, h=h, w=wd, cin=cin, cout=cout, stride=int(stride), residual=residual is not None,
+               upsample=upsample is not None, out_mode=out_mode)
     return out
 
 
@@ -89,6 +106,7 @@ def lower_conv(x, ksize, stride, pad, kpad=None, relu=False):
     _lib.check(_lib.lib().odtk_lower_conv(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
                                           ksize, stride, pad, kpad, int(relu), _stream()), "lower_conv")
     STATS["launches"] += 1
+    _trace("lower_conv", 0, x.numel() * 2 + out.numel() * 2, n=n, h=h, w=w, cin=c)
     return out
 
 
@@ -98,6 +116,7 @@ def maxpool3x3s2(x):
     _lib.check(_lib.lib().odtk_maxpool3x3s2(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w, c,
                                             _stream()), "maxpool3x3s2")
     STATS["launches"] += 1
+    _trace("maxpool", 0, x.numel() * 2 + out.numel() * 2, n=n, h=h, w=w, cin=c)
     return out
 
 
@@ -125,6 +144,7 @@ def preprocess_u8(images, stride=128, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     _lib.check(_lib.lib().odtk_preprocess_u8(ctypes.c_void_p(images.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, w,
                                              hs, ws, m, s, _stream()), "preprocess_u8")
     STATS["launches"] += 1
+    _trace("preprocess_u8", 0, images.numel() + xp.numel() * 2, n=n, h=h, w=w, cin=3)
     return xp, hs, ws
 
 
@@ -136,6 +156,8 @@ def stem_conv_padded(xp, h, wd, w, bias, cout, relu=True):
                                          ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
                                          ctypes.c_void_p(out.data_ptr()), n, h, wd, cout, int(relu), _stream()), "stem_conv")
     STATS["launches"] += 1
+    _trace("stem7x7", 2 * out.numel() * 147, xp.numel() * 2 + w.numel() * 2 + out.numel() * 2, n=n, h=h, w=wd, cin=3,
+           cout=cout, stride=2)
     return out
 
 
@@ -153,4 +175,7 @@ def stem_conv(x, w, bias, cout, relu=True):
                                 ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
                                 ctypes.c_void_p(out.data_ptr()), n, h, wd, cout, int(relu), _stream()), "stem_conv")
     STATS["launches"] += 2
+    _trace("pad_input", 0, x.numel() * 2 + xp.numel() * 2, n=n, h=h, w=wd, cin=3)
+    _trace("stem7x7", 2 * out.numel() * 147, xp.numel() * 2 + w.numel() * 2 + out.numel() * 2, n=n, h=h, w=wd, cin=3,
+           cout=cout, stride=2)
     return out
