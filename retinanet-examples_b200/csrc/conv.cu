@@ -203,9 +203,26 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr, uint32_t l
   return d;
 }
 
+// Halo mode: view of the patch [18][16 pixels][64 ch] (pixel pitch 128 B, patch-row pitch 2048 B) shifted by a tap.
+// 8-row groups (8 consecutive pixels) are 2048 B apart; the 128-byte swizzle phase of the first row is
+// (start >> 7) & 7: the tensor core derives it from the absolute shared-memory address, exactly as the TMA unit did
+// when it wrote the patch, so the base-offset field [49,52) stays 0 (setting it shifts the phase twice: measured).
+constexpr int kPatchBytes = 18 * 16 * 128;
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int use_boff) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(2048 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (use_boff) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 struct Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t patch_full[3], patch_empty[3];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full, res_empty, ident_full;   // residual-on-the-tensor-core path
@@ -239,6 +256,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL2 ? 2 : 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], (TWO ? 2 : 1) * 32 * kEpiWarps); }
     mbar_init(&bars->res_full, 1); mbar_init(&bars->res_empty, 1); mbar_init(&bars->ident_full, 1);
+    for (int s = 0; s < 3; s++) { mbar_init(&bars->patch_full[s], 1); mbar_init(&bars->patch_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -292,6 +310,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
         tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
       }
+      if (p.mode == 4) {
+        // ---- halo mode: one patch load per (tile, 64-channel chunk), nine weight blocks behind it ----
+        unsigned char *sones = smem + p.npatch * kPatchBytes;
+        unsigned char *sbst = sones + (p.bias_mma ? kABytes : 0);
+        const uint32_t bstage = b_bytes;
+        if (p.bias_mma) {   // constant A operand of the bias block, loaded once
+          if (TWO) {
+            if (crank == 0) mbar_arrive_expect_tx(&bars->ident_full, 2u * kABytes);
+            tma2_load_2d(sones, &tmOnes, mapa_rank(smem_u32(&bars->ident_full), 0), 0, 0);
+          } else {
+            mbar_arrive_expect_tx(&bars->ident_full, (uint32_t)kABytes);
+            tma_load_2d(sones, &tmOnes, &bars->ident_full, 0, 0);
+          }
+        }
+        int pb = 0;
+        uint32_t pphase = 0;
+        const int per_img = p.tiles_h * p.tiles_w, half = p.BN >> 1;
+        for (int tile = w_first; tile < w_total; tile += w_step) {
+          int m_tile, n_tile;
+          work_tile(tile, m_tile, n_tile);
+          const int n0 = n_tile * p.BN;
+          const int img = m_tile / per_img, rr = m_tile - img * per_img;
+          const int h0 = (rr / p.tiles_w) * p.TH, w0 = (rr % p.tiles_w) * p.TW;
+          const int c1 = p.tile_t ? h0 - 1 : w0 - 1, c2 = p.tile_t ? w0 - 1 : h0 - 1;
+          for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
+            mbar_wait(&bars->patch_empty[pb], pphase ^ 1u);
+            unsigned char *dst = smem + pb * kPatchBytes;
+            if (TWO) {
+              if (crank == 0) mbar_arrive_expect_tx(&bars->patch_full[pb], 2u * kPatchBytes);
+              tma2_load_4d(dst, &tmA, mapa_rank(smem_u32(&bars->patch_full[pb]), 0), kc * 64, c1, c2, img);
+            } else {
+              mbar_arrive_expect_tx(&bars->patch_full[pb], (uint32_t)kPatchBytes);
+              tma_load_4d(dst, &tmA, &bars->patch_full[pb], kc * 64, c1, c2, img);
+            }
+            if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
+            for (int tap = 0; tap < 9; tap++) {
+              mbar_wait(&bars->empty[stage], phase ^ 1u);
+              unsigned char *sb = sbst + stage * bstage;
+              if (TWO) {
+                if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
+                tma2_load_2d(sb, &tmB, mapa_rank(smem_u32(&bars->full[stage]), 0), (tap * p.kblocks_per_tap + kc) * 64, n0 + crank * half);
+              } else {
+                mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
+                tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kc) * 64, n0);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (p.bias_mma) {
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            unsigned char *sb = sbst + stage * bstage;
+            if (TWO) {
+              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
+              tma2_load_2d(sb, &tmBias, mapa_rank(smem_u32(&bars->full[stage]), 0), 0, n0 + crank * half);
+            } else {
+              mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
+              tma_load_2d(sb, &tmBias, &bars->full[stage], 0, n0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else
       for (int tile = w_first; tile < w_total; tile += w_step) {
         int m_tile, n_tile;
         work_tile(tile, m_tile, n_tile);
@@ -385,6 +465,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       const uint32_t sres = smem_u32(smem + 2 * (kABytes + kBBytesMax)), sident = sres + 4 * kABytes;
       if (p.res_mma) mbar_wait(&bars->ident_full, 0);
+      if (p.mode == 4) {
+        const uint32_t sones = smem_u32(smem + p.npatch * kPatchBytes);
+        const uint32_t sbst = sones + (p.bias_mma ? (uint32_t)kABytes : 0u);
+        if (p.bias_mma) mbar_wait(&bars->ident_full, 0);
+        int pb = 0;
+        uint32_t pphase = 0;
+        for (int tile = w_first; tile < w_total; tile += w_step, it++) {
+          const int buf = it & 1;
+          mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+          for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
+            mbar_wait(&bars->patch_full[pb], pphase);
+            tc_fence_after();
+            const uint32_t pbase = smem_u32(smem + pb * kPatchBytes);
+            for (int tap = 0; tap < 9; tap++) {
+              mbar_wait(&bars->full[stage], phase);
+              tc_fence_after();
+              const int r = tap / 3, s3 = tap - 3 * r;
+              const uint32_t off = (uint32_t)(p.tile_t ? s3 * 16 + r : r * 16 + s3) * 128u;
+              const uint64_t da = make_desc_halo(pbase + off, p.halo_boff);
+              const uint64_t db = make_desc_kmajor(sbst + (uint32_t)stage * b_bytes, 128);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+                else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+              }
+              if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            if (TWO) tc_commit2_mc(&bars->patch_empty[pb], (uint16_t)3); else tc_commit(&bars->patch_empty[pb]);
+            if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
+          }
+          if (p.bias_mma) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_desc_kmajor(sones, 128), db = make_desc_kmajor(sbst + (uint32_t)stage * b_bytes, 128);
+            if (TWO) tc_mma2_f16(tmem_d, da, db, idesc, 1u); else tc_mma_f16(tmem_d, da, db, idesc, 1u);
+            if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]);
+        }
+      } else
       for (int tile = w_first; tile < w_total; tile += w_step, it++) {
         const int buf = it & 1;
         mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -449,11 +573,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
     int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
     if (p.mode != 0) { own_dh = row / p.TW; own_dw = row - own_dh * p.TW; }
+    if (p.tile_t) { own_dh = row & 7; own_dw = row >> 3; }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int rr = q * 32 + k * rpi + sub;
       dh8[k] = (p.mode != 0) ? rr / p.TW : 0;
       dw8[k] = (p.mode != 0) ? rr - dh8[k] * p.TW : rr;
+      if (p.tile_t) { dh8[k] = rr & 7; dw8[k] = rr >> 3; }
     }
     int pix8[8];
     uint4 pre[8];
@@ -965,13 +1091,42 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   } else {
     p.mode = 1;
     choose_patch(d->h, d->width, p.TH, p.TW);
+    // halo mode: fixed 16x8 (or transposed 8x16) pixel tiles; used when they waste few more accumulator rows
+    // than the free-form patch (the nine-fold smaller input traffic from L2 pays for up to ~15 %)
+    static int halo_on = -1, halo_boff = 0;
+    if (halo_on < 0) {
+      const char *e = getenv("ODTK_CONV_HALO"); halo_on = e ? atoi(e) : 1;
+      const char *b = getenv("ODTK_CONV_HALO_BOFF"); halo_boff = b ? atoi(b) : 0;   // measured on B200: the swizzle phase follows the absolute address, base offset must stay 0
+    }
+    const double hw = (double)d->h * d->width;
+    const double eff_free = hw / ((double)((d->h + p.TH - 1) / p.TH) * ((d->width + p.TW - 1) / p.TW) * 128.0);
+    const double eff_a = hw / ((double)((d->h + 15) / 16) * ((d->width + 7) / 8) * 128.0);
+    const double eff_b = hw / ((double)((d->h + 7) / 8) * ((d->width + 15) / 16) * 128.0);
+    // row-major tiles keep the fp32 NCHW stores of the head outputs in 32-byte runs: prefer them there
+    const bool transposed = (p.out_mode == ODTK_OUT_NHWC_F16) ? eff_b > eff_a + 1e-9 : eff_b > 1.15 * eff_a;
+    const double eff_halo = transposed ? eff_b : eff_a;
+    if (halo_on && eff_halo >= 0.84 * eff_free && d->h >= 8 && d->width >= 8) {
+      p.mode = 4;
+      p.tile_t = transposed ? 1 : 0;
+      p.halo_boff = halo_boff;
+      p.TH = transposed ? 8 : 16;
+      p.TW = transposed ? 16 : 8;
+    }
     p.tiles_h = (d->h + p.TH - 1) / p.TH;
     p.tiles_w = (d->width + p.TW - 1) / p.TW;
     p.num_m_tiles = d->n * p.tiles_h * p.tiles_w;
-    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->h, (uint64_t)d->n};
-    uint64_t str[3] = {(uint64_t)d->cin * 2, (uint64_t)d->width * d->cin * 2, (uint64_t)d->h * d->width * d->cin * 2};
-    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-    if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
+    const uint64_t C = (uint64_t)d->cin, W = (uint64_t)d->width, H = (uint64_t)d->h;
+    if (p.mode == 4 && p.tile_t) {   // patch stored [18 columns][16-row pitch][64 ch]: H is the faster box dimension
+      uint64_t dims[4] = {C, H, W, (uint64_t)d->n};
+      uint64_t str[3] = {W * C * 2, C * 2, H * W * C * 2};
+      uint32_t box[4] = {64, 16, 18, 1};
+      if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
+    } else {
+      uint64_t dims[4] = {C, W, H, (uint64_t)d->n};
+      uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+      uint32_t box[4] = {64, (uint32_t)(p.mode == 4 ? 16 : p.TW), (uint32_t)(p.mode == 4 ? 18 : p.TH), 1};
+      if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
+    }
   }
   // wide 1x1 outputs (the memory-bound layers): the epilogue hands its staged slabs to the TMA unit
   CUtensorMap tmC = tmB;
@@ -998,7 +1153,8 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   // 2-CTA clusters with weight multicast: the compute-bound 256-wide layers with enough tiles for every cluster
   static int cluster_on = -1;
   if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 2; }   // 0 off, 1 multicast, 2 cta_group::2
-  if (cluster_on && BN > 128 && !d->upsample && !d->residual && (p.mode == 0 || p.mode == 1 || p.mode == 3) &&
+  if (cluster_on && BN > 128 && !d->upsample && !d->residual &&
+      (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
     uint64_t dims[2] = {Kw, (uint64_t)d->cout}, str[1] = {Kw * 2};
@@ -1031,6 +1187,14 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
       p.res_mma = 1;
       p.nstages = 2;   // the rest of the pipeline region holds the residual tile (64 KB) and the identity (32 KB)
     }
+  }
+  if (p.mode == 4) {   // pipeline region: patches | ones tile (bias block) | weight-block stages
+    const int bstage = (p.cluster2 == 2 ? BN / 2 : BN) * 128;
+    const int fixed = p.bias_mma ? kABytes : 0;
+    p.npatch = (kPipeBytes - fixed - 3 * kPatchBytes) / bstage >= 6 ? 3 : 2;
+    p.nstages = (kPipeBytes - fixed - p.npatch * kPatchBytes) / bstage;
+    if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+    if (p.nstages < 2) return ODTK_E_UNSUPPORTED;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;

@@ -21,6 +21,12 @@ struct ConvParams {
   int bias_mma;         // the bias is added by one extra K block on the tensor core (A = ones, B = bias hi/lo)
   int tma_store;        // epilogue hands 32x64 slabs to cp.async.bulk.tensor stores (mode 0, BN > 128)
   int nstages;          // pipeline stages that fit: (16 KB + BN*128 B) each
+  // mode 4 ("halo"): 3x3 stride-1 conv whose input patch (18 x 16-pixel pitch x 64 channels, 36 KB) is loaded ONCE per
+  // 64-channel chunk; the nine taps are nine shifted shared-memory views of it (UMMA descriptors, 2048-byte group stride)
+  int npatch;           // patch buffers (2 or 3); the weight-block stages follow them in the pipeline region
+  int tile_t;           // 0: tile = 16 rows x 8 columns of pixels (accumulator row m -> (m / 8, m % 8));
+                        // 1: transposed, 8 rows x 16 columns (m -> (m % 8, m / 8)), patch stored column-major
+  int halo_boff;        // put (start address >> 7) & 7 into the descriptor's base-offset field
   // out_mode ODTK_OUT_CANDIDATES: the decode workspace of this pyramid level (decode.cu)
   int *cand_counts;          // [N]
   unsigned *cand_hist;       // [N, cand_hist_bins]
