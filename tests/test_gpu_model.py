@@ -119,7 +119,7 @@ def test_parallel_head_streams_equal_sequential():
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("threshold,top_n", [(0.05, 1000), (0.0, 300), (None, 50), (0.02, 4096)])
+@pytest.mark.parametrize("threshold,top_n", [(0.05, 1000), (0.0, 300), (None, 50), (0.02, 1200)])
 def test_fused_candidate_epilogue_equals_dense_route(threshold, top_n):
     """The class head's last convolution appending candidates itself (ODTK_OUT_CANDIDATES +
     odtk_decode_fused_*) must give bit-identical detections to dense score maps + odtk_decode_levels;
