@@ -284,14 +284,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int w_step = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int w_total = CLUSTER ? mpairs * p.num_n_tiles : total_tiles;
   auto work_tile = [&](int wi, int &m_tile, int &n_tile) -> bool {   // returns false for the padding tile of an odd pair
+    // N fastest: the CTAs that run concurrently share their input rows (one DRAM read, L2 hits for the other N
+    // tiles); the weights of all N tiles stay L2-resident anyway
     if (CLUSTER) {
-      n_tile = wi / mpairs;
-      m_tile = 2 * (wi - n_tile * mpairs) + crank;
+      const int pair = wi / p.num_n_tiles;
+      n_tile = wi - pair * p.num_n_tiles;
+      m_tile = 2 * pair + crank;
       if (m_tile >= p.num_m_tiles) { m_tile = p.num_m_tiles - 1; return false; }
       return true;
     }
-    m_tile = wi % p.num_m_tiles;
-    n_tile = wi / p.num_m_tiles;
+    m_tile = wi / p.num_n_tiles;
+    n_tile = wi - m_tile * p.num_n_tiles;
     return true;
   };
   const int kblocks = p.taps * p.kblocks_per_tap;
@@ -668,7 +671,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               // last segment of this tile: the write-out below goes through the TMA unit and no longer
               // needs pix8, so fetch the addend of the NEXT tile's first segment now -- its DRAM latency
               // then overlaps this segment's maths and the wait for the next accumulator
-              const int nt = tile + w_step, m2 = nt % p.num_m_tiles, n2 = nt / p.num_m_tiles;
+              const int nt = tile + w_step, m2 = nt / p.num_n_tiles, n2 = nt - m2 * p.num_n_tiles;
 #pragma unroll
               for (int k = 0; k < 8; k++) {
                 const int m = m2 * 128 + dw8[k];
@@ -1153,7 +1156,9 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   // 2-CTA clusters with weight multicast: the compute-bound 256-wide layers with enough tiles for every cluster
   static int cluster_on = -1;
   if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 2; }   // 0 off, 1 multicast, 2 cta_group::2
-  if (cluster_on && BN > 128 && !d->upsample && !d->residual &&
+  static int cluster_1x1 = -1;
+  if (cluster_1x1 < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_1X1"); cluster_1x1 = e ? atoi(e) : 1; }
+  if (cluster_on && BN > 128 && !d->upsample && !d->residual && (cluster_1x1 || d->ksize == 3) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
