@@ -135,6 +135,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// One lane of a fully converged warp.  The issuing warps stay converged and wrap only the TMA / MMA / commit
+// instructions in `if (elect_one())`: their operands then live in uniform registers, instead of the per-instruction
+// "waterfall" loops (ELECT + R2UR.BROADCAST + branch) the compiler emits around them in lane-0-only code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -245,7 +253,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   Barriers *bars = reinterpret_cast<Barriers *>(smem + kPipeBytes + kEpiWarps * kSlabBytes);
   constexpr bool CL2 = (CL == 1), TWO = (CL == 2), CLUSTER = (CL != 0);
   const int kStages = p.nstages, kStageBytes = kABytes + (TWO ? p.BN >> 1 : p.BN) * 128;   // per-layer pipeline geometry
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -303,12 +311,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {   // whole warp converged; one elected lane arms the barriers and issues the TMA loads
       int stage = 0;
       uint32_t phase = 0, rphase = 0;
       unsigned char *sres = smem + 2 * (kABytes + kBBytesMax);          // 64 KB residual tile (res_mma: 2 stages only)
       unsigned char *sident = sres + 4 * kABytes;                        // 32 KB identity
-      if (p.res_mma) {
+      if (p.res_mma && elect_one()) {
         mbar_arrive_expect_tx(&bars->ident_full, 2u * kABytes);
         tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
         tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
@@ -318,7 +326,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         unsigned char *sones = smem + p.npatch * kPatchBytes;
         unsigned char *sbst = sones + (p.bias_mma ? kABytes : 0);
         const uint32_t bstage = b_bytes;
-        if (p.bias_mma) {   // constant A operand of the bias block, loaded once
+        if (p.bias_mma && elect_one()) {   // constant A operand of the bias block, loaded once
           if (TWO) {
             if (crank == 0) mbar_arrive_expect_tx(&bars->ident_full, 2u * kABytes);
             tma2_load_2d(sones, &tmOnes, mapa_rank(smem_u32(&bars->ident_full), 0), 0, 0);
@@ -340,23 +348,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
             mbar_wait(&bars->patch_empty[pb], pphase ^ 1u);
             unsigned char *dst = smem + pb * kPatchBytes;
-            if (TWO) {
-              if (crank == 0) mbar_arrive_expect_tx(&bars->patch_full[pb], 2u * kPatchBytes);
-              tma2_load_4d(dst, &tmA, mapa_rank(smem_u32(&bars->patch_full[pb]), 0), kc * 64, c1, c2, img);
-            } else {
-              mbar_arrive_expect_tx(&bars->patch_full[pb], (uint32_t)kPatchBytes);
-              tma_load_4d(dst, &tmA, &bars->patch_full[pb], kc * 64, c1, c2, img);
+            if (elect_one()) {
+              if (TWO) {
+                if (crank == 0) mbar_arrive_expect_tx(&bars->patch_full[pb], 2u * kPatchBytes);
+                tma2_load_4d(dst, &tmA, mapa_rank(smem_u32(&bars->patch_full[pb]), 0), kc * 64, c1, c2, img);
+              } else {
+                mbar_arrive_expect_tx(&bars->patch_full[pb], (uint32_t)kPatchBytes);
+                tma_load_4d(dst, &tmA, &bars->patch_full[pb], kc * 64, c1, c2, img);
+              }
             }
             if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
             for (int tap = 0; tap < 9; tap++) {
               mbar_wait(&bars->empty[stage], phase ^ 1u);
               unsigned char *sb = sbst + stage * bstage;
-              if (TWO) {
-                if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
-                tma2_load_2d(sb, &tmB, mapa_rank(smem_u32(&bars->full[stage]), 0), (tap * p.kblocks_per_tap + kc) * 64, n0 + crank * half);
-              } else {
-                mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
-                tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kc) * 64, n0);
+              if (elect_one()) {
+                if (TWO) {
+                  if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
+                  tma2_load_2d(sb, &tmB, mapa_rank(smem_u32(&bars->full[stage]), 0), (tap * p.kblocks_per_tap + kc) * 64, n0 + crank * half);
+                } else {
+                  mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
+                  tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kc) * 64, n0);
+                }
               }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
@@ -364,12 +376,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.bias_mma) {
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             unsigned char *sb = sbst + stage * bstage;
-            if (TWO) {
-              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
-              tma2_load_2d(sb, &tmBias, mapa_rank(smem_u32(&bars->full[stage]), 0), 0, n0 + crank * half);
-            } else {
-              mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
-              tma_load_2d(sb, &tmBias, &bars->full[stage], 0, n0);
+            if (elect_one()) {
+              if (TWO) {
+                if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * b_bytes);
+                tma2_load_2d(sb, &tmBias, mapa_rank(smem_u32(&bars->full[stage]), 0), 0, n0 + crank * half);
+              } else {
+                mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
+                tma_load_2d(sb, &tmBias, &bars->full[stage], 0, n0);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -397,34 +411,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (TWO) {
               // cta_group::2: both CTAs load their own A rows and their half of the weight rows into their own
               // shared memory; every byte is counted on the LEADER's barrier, which the leader arms for the pair
-              const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
-              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (a_bytes + b_bytes));
-              const int half = p.BN >> 1;
-              if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, w0 + dx, h0 + dy, img);
-              else if (p.mode == 3) {
-                const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
-                tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
-              } else                tma2_load_2d(sa, &tmA, lbar, kb * 64, m_tile * 128);
-              tma2_load_2d(sb, &tmB, lbar, (tap * p.kblocks_per_tap + kb) * kelems, n0 + crank * half);
+              if (elect_one()) {
+                const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
+                if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (a_bytes + b_bytes));
+                const int half = p.BN >> 1;
+                if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, w0 + dx, h0 + dy, img);
+                else if (p.mode == 3) {
+                  const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
+                  tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
+                } else                tma2_load_2d(sa, &tmA, lbar, kb * 64, m_tile * 128);
+                tma2_load_2d(sb, &tmB, lbar, (tap * p.kblocks_per_tap + kb) * kelems, n0 + crank * half);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
               continue;
             }
-            mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
-            if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
-            else if (p.mode == 3) {
-              // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
-              const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
-              tma_load_5d(sa, &tmA, &bars->full[stage], pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph,
-                          h0 + (dy < 0 ? -1 : 0), img);
-            }
-            else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
-            else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
-            if (CL2) {   // each CTA fetches half of the weight rows and multicasts them to both
-              const int half = p.BN >> 1;
-              tma_load_2d_mc(sb + crank * half * p.row_bytes, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems,
-                             n0 + crank * half, (uint16_t)3);
-            } else {
-              tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
+              if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
+              else if (p.mode == 3) {
+                // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
+                const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
+                tma_load_5d(sa, &tmA, &bars->full[stage], pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph,
+                            h0 + (dy < 0 ? -1 : 0), img);
+              }
+              else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
+              else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
+              if (CL2) {   // each CTA fetches half of the weight rows and multicasts them to both
+                const int half = p.BN >> 1;
+                tma_load_2d_mc(sb + crank * half * p.row_bytes, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems,
+                               n0 + crank * half, (uint16_t)3);
+              } else {
+                tma_load_2d(sb, &tmB, &bars->full[stage], (tap * p.kblocks_per_tap + kb) * kelems, n0);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -434,16 +452,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // the tensor core adds the fp32 bias (split into two fp16 terms, exact to 2^-22) for free
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           unsigned char *sa = smem + stage * kStageBytes;
-          if (TWO) {
-            const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
-            if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * ((uint32_t)kABytes + b_bytes));
-            tma2_load_2d(sa, &tmOnes, lbar, 0, 0);
-            tma2_load_2d(sa + kABytes, &tmBias, lbar, 0, n0 + crank * (p.BN >> 1));
-          } else {
-          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + b_bytes);
-          tma_load_2d(sa, &tmOnes, &bars->full[stage], 0, 0);
-          if (CL2) tma_load_2d_mc(sa + kABytes + crank * (p.BN >> 1) * 128, &tmBias, &bars->full[stage], 0, n0 + crank * (p.BN >> 1), (uint16_t)3);
-          else     tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
+          if (elect_one()) {
+            if (TWO) {
+              const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * ((uint32_t)kABytes + b_bytes));
+              tma2_load_2d(sa, &tmOnes, lbar, 0, 0);
+              tma2_load_2d(sa + kABytes, &tmBias, lbar, 0, n0 + crank * (p.BN >> 1));
+            } else {
+              mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + b_bytes);
+              tma_load_2d(sa, &tmOnes, &bars->full[stage], 0, 0);
+              if (CL2) tma_load_2d_mc(sa + kABytes + crank * (p.BN >> 1) * 128, &tmBias, &bars->full[stage], 0, n0 + crank * (p.BN >> 1), (uint16_t)3);
+              else     tma_load_2d(sa + kABytes, &tmBias, &bars->full[stage], 0, n0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -451,16 +471,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // residual tile [128 pixels x 256 channels] as four 128B-swizzled 64-channel slices: it becomes the
           // MN-major B operand of D += I * R (identity times residual), i.e. the tensor core does the add
           mbar_wait(&bars->res_empty, rphase ^ 1u);
-          mbar_arrive_expect_tx(&bars->res_full, 4u * kABytes);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->res_full, 4u * kABytes);
 #pragma unroll
-          for (int j = 0; j < 4; j++) tma_load_2d(sres + j * kABytes, &tmRes, &bars->res_full, n0 + 64 * j, m_tile * 128);
+            for (int j = 0; j < 4; j++) tma_load_2d(sres + j * kABytes, &tmRes, &bars->res_full, n0 + 64 * j, m_tile * 128);
+          }
           rphase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0 && (!TWO || crank == 0)) {   // cta_group::2: the leader CTA issues for the pair
+    if (!TWO || crank == 0) {   // cta_group::2: the leader CTA issues for the pair; whole warp converged, one elected lane issues
       // instruction descriptor: D=f32, A=B=f16, both K-major, N = BN, M = 128 (256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);
       int stage = 0;
@@ -490,26 +512,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t off = (uint32_t)(p.tile_t ? s3 * 16 + r : r * 16 + s3) * 128u;
               const uint64_t da = make_desc_halo(pbase + off, p.halo_boff);
               const uint64_t db = make_desc_kmajor(sbst + (uint32_t)stage * b_bytes, 128);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
-                else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+                for (int k = 0; k < 4; k++) {
+                  if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+                  else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+                }
+                if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+                if (tap == 8) { if (TWO) tc_commit2_mc(&bars->patch_empty[pb], (uint16_t)3); else tc_commit(&bars->patch_empty[pb]); }
               }
-              if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            if (TWO) tc_commit2_mc(&bars->patch_empty[pb], (uint16_t)3); else tc_commit(&bars->patch_empty[pb]);
             if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
           }
           if (p.bias_mma) {
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
             const uint64_t da = make_desc_kmajor(sones, 128), db = make_desc_kmajor(sbst + (uint32_t)stage * b_bytes, 128);
-            if (TWO) tc_mma2_f16(tmem_d, da, db, idesc, 1u); else tc_mma_f16(tmem_d, da, db, idesc, 1u);
-            if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+            if (elect_one()) {
+              if (TWO) tc_mma2_f16(tmem_d, da, db, idesc, 1u); else tc_mma_f16(tmem_d, da, db, idesc, 1u);
+              if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]);
+          if (elect_one()) { if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]); }
         }
       } else
       for (int tile = w_first; tile < w_total; tile += w_step, it++) {
@@ -524,13 +550,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_desc_kmajor(sa, p.row_bytes), db = make_desc_kmajor(sa + kABytes, p.row_bytes);
           const int ksteps = (kb == kblocks) ? 1 : (p.row_bytes >> 5);   // UMMA_K(16) steps per block (+32 B each); the bias block has one
-          for (int k = 0; k < ksteps; k++) {
-            if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-            else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; k++) {
+              if (TWO) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              else     tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            }
+            if (TWO)      tc_commit2_mc(&bars->empty[stage], (uint16_t)3);
+            else if (CL2) tc_commit_mc(&bars->empty[stage], (uint16_t)3);
+            else          tc_commit(&bars->empty[stage]);
           }
-          if (TWO)      tc_commit2_mc(&bars->empty[stage], (uint16_t)3);
-          else if (CL2) tc_commit_mc(&bars->empty[stage], (uint16_t)3);
-          else          tc_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_mma) {
@@ -538,15 +566,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           rphase ^= 1u;
           const uint32_t idesc_r = idesc | (1u << 16);     // B operand MN-major
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) {   // K = 128 pixels of the tile, 16 per instruction
-            const uint64_t da = make_desc_kmajor(sident + (uint32_t)(j >> 2) * kABytes, 128) + (uint64_t)(2 * (j & 3));
-            const uint64_t db = make_desc_mnmajor(sres + (uint32_t)j * 2048u, (uint32_t)kABytes);
-            tc_mma_f16(tmem_d, da, db, idesc_r, 1u);
+            for (int j = 0; j < 8; j++) {   // K = 128 pixels of the tile, 16 per instruction
+              const uint64_t da = make_desc_kmajor(sident + (uint32_t)(j >> 2) * kABytes, 128) + (uint64_t)(2 * (j & 3));
+              const uint64_t db = make_desc_mnmajor(sres + (uint32_t)j * 2048u, (uint32_t)kABytes);
+              tc_mma_f16(tmem_d, da, db, idesc_r, 1u);
+            }
+            tc_commit(&bars->res_empty);
           }
-          tc_commit(&bars->res_empty);
         }
-        if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]);
+        if (elect_one()) { if (TWO) tc_commit2_mc(&bars->tmem_full[buf], (uint16_t)3); else tc_commit(&bars->tmem_full[buf]); }
       }
     }
   } else if (warp >= 4) {
@@ -1157,7 +1187,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   static int cluster_on = -1;
   if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 2; }   // 0 off, 1 multicast, 2 cta_group::2
   static int cluster_1x1 = -1;
-  if (cluster_1x1 < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_1X1"); cluster_1x1 = e ? atoi(e) : 1; }
+  if (cluster_1x1 < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_1X1"); cluster_1x1 = e ? atoi(e) : 0; }   // measured: 1x1 layers are faster unclustered with the TMA-store epilogue (+2.6 % per step)
   if (cluster_on && BN > 128 && !d->upsample && !d->residual && (cluster_1x1 || d->ksize == 3) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
