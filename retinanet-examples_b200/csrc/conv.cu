@@ -227,6 +227,24 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int use_boff)
   return d;
 }
 
+// Stem "raw window" mode: the A operand is read straight out of the zero-padded NHWC4 image patch in shared memory.
+// Un-swizzled K-major canonical layout ((8,m),(8,2k)) : ((16 B, SBO),(1, LBO)): the 8 rows of a core matrix are 16 B
+// apart -- exactly the distance between the windows of neighbouring output pixels (stride 2 x 4 channels x 2 B) -- the
+// next 16-byte K chunk of a row is LBO = 16 B further (= chunk 0 of the next pixel: the windows overlap), and the next
+// group of 8 output pixels (one output row down) is SBO = two patch rows further.
+constexpr int kStemPatchW = 24;                         // padded pixels per patch row: 2*8 + 6, rounded to the 16-byte pair
+constexpr int kStemPatchRowBytes = kStemPatchW * 8;     // 192
+constexpr int kStemPatchBytes = 37 * kStemPatchRowBytes;  // 2*16 + 5 rows
+constexpr int kStemPatchSlot = 8192;
+__device__ __forceinline__ uint64_t make_desc_raw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                             // layout type 0: no swizzle
+}
+
 struct Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -321,7 +339,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
         tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
       }
-      if (p.mode == 4) {
+      if (p.mode == 5) {
+        // ---- stem, raw-window mode: the 28 KB of weights stay resident; one 7 KB image patch per tile ----
+        unsigned char *sw = smem + kMaxStages * kStemPatchSlot;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->ident_full, 7u * (uint32_t)(p.BN * 64));
+          for (int r = 0; r < 7; r++) tma_load_2d(sw + r * (p.BN * 64), &tmB, &bars->ident_full, r * 32, 0);
+        }
+        const int per_img = p.tiles_h * p.tiles_w;
+        for (int tile = w_first; tile < w_total; tile += w_step) {
+          const int img = tile / per_img, rr = tile - img * per_img;
+          const int h0 = (rr / p.tiles_w) * 16, w0 = (rr % p.tiles_w) * 8;
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kStemPatchBytes);
+            tma_load_4d(smem + stage * kStemPatchSlot, &tmA, &bars->full[stage], 0, w0, 2 * h0, img);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      } else if (p.mode == 4) {
         // ---- halo mode: one patch load per (tile, 64-channel chunk), nine weight blocks behind it ----
         unsigned char *sones = smem + p.npatch * kPatchBytes;
         unsigned char *sbst = sones + (p.bias_mma ? kABytes : 0);
@@ -490,7 +526,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       const uint32_t sres = smem_u32(smem + 2 * (kABytes + kBBytesMax)), sident = sres + 4 * kABytes;
       if (p.res_mma) mbar_wait(&bars->ident_full, 0);
-      if (p.mode == 4) {
+      if (p.mode == 5) {
+        const uint32_t sw = smem_u32(smem + kMaxStages * kStemPatchSlot);
+        mbar_wait(&bars->ident_full, 0);
+        for (int tile = w_first; tile < w_total; tile += w_step, it++) {
+          const int buf = it & 1;
+          mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(smem + stage * kStemPatchSlot);
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+#pragma unroll
+              for (int k = 0; k < 2; k++) {   // 16 K elements = 4 padded pixels x 4 channels = 32 B of the window
+                const uint64_t da = p.halo_boff ? make_desc_raw(patch + r * kStemPatchRowBytes + k * 32, 2u * kStemPatchRowBytes, 16u)
+                                                : make_desc_raw(patch + r * kStemPatchRowBytes + k * 32, 16u, 2u * kStemPatchRowBytes);
+                const uint64_t db = make_desc_kmajor(sw + (uint32_t)(r * p.BN * 64), 64) + (uint64_t)(2 * k);
+                tc_mma_f16(tmem_d, da, db, idesc, (r | k) ? 1u : 0u);
+              }
+            }
+            tc_commit(&bars->empty[stage]);
+            tc_commit(&bars->tmem_full[buf]);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      } else if (p.mode == 4) {
         const uint32_t sones = smem_u32(smem + p.npatch * kPatchBytes);
         const uint32_t sbst = sones + (p.bias_mma ? (uint32_t)kABytes : 0u);
         if (p.bias_mma) mbar_wait(&bars->ident_full, 0);
@@ -1273,11 +1336,25 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
   p.bias = bias; p.out = y; p.relu = relu; p.out_mode = ODTK_OUT_NHWC_F16; p.ldy = cout; p.ldr = cout;
   choose_patch(OH, OW, p.TH, p.TW);
+  // raw-window mode: 16 x 8 output-pixel tiles whose A operand is an un-swizzled view of the padded image patch
+  static int stem_raw = -1, stem_swap = 0;
+  if (stem_raw < 0) {
+    const char *e = getenv("ODTK_STEM_RAW"); stem_raw = e ? atoi(e) : 1;
+    const char *f = getenv("ODTK_STEM_RAW_SWAP"); stem_swap = f ? atoi(f) : 0;   // diagnostic: swap LBO / SBO
+  }
+  const bool raw = stem_raw && cout <= 128 && kMaxStages * kStemPatchSlot + 7 * cout * 64 <= kPipeBytes;
+  if (raw) { p.mode = 5; p.TH = 16; p.TW = 8; p.nstages = kMaxStages; p.halo_boff = stem_swap; }
   p.tiles_h = (OH + p.TH - 1) / p.TH;
   p.tiles_w = (OW + p.TW - 1) / p.TW;
   p.num_m_tiles = n * p.tiles_h * p.tiles_w;
   CUtensorMap tmA, tmB;
-  {
+  if (raw) {
+    // padded image [n, HP, WP, 4] viewed as 16-byte pixel pairs: {8 el, WP/2, HP, n}; patch = 12 pairs x 37 rows
+    uint64_t dims[4] = {8, (uint64_t)WP / 2, (uint64_t)HP, (uint64_t)n};
+    uint64_t str[3] = {16, (uint64_t)WP * 8, (uint64_t)HP * WP * 8};
+    uint32_t box[4] = {8, kStemPatchW / 2, 37, 1};
+    if (!encode_map(&tmA, xp, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return ODTK_E_UNSUPPORTED;
+  } else {
     uint64_t dims[5] = {32, (uint64_t)OW, 7, (uint64_t)OH, (uint64_t)n};
     uint64_t str[4] = {16, (uint64_t)WP * 8, (uint64_t)WP * 16, (uint64_t)HP * WP * 8};
     uint32_t box[5] = {32, (uint32_t)p.TW, 1, (uint32_t)p.TH, 1};
