@@ -371,6 +371,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sones, &tmOnes, &bars->ident_full, 0, 0);
           }
         }
+        if (p.b_resident && elect_one()) {   // small layers (64 -> 64): every weight block stays in shared memory
+          const int nb = 9 * p.kblocks_per_tap;
+          mbar_arrive_expect_tx(&bars->res_full, (uint32_t)(nb + (p.bias_mma ? 1 : 0)) * b_bytes);
+          for (int j = 0; j < nb; j++) tma_load_2d(sbst + j * bstage, &tmB, &bars->res_full, j * 64, 0);
+          if (p.bias_mma) tma_load_2d(sbst + nb * bstage, &tmBias, &bars->res_full, 0, 0);
+        }
         int pb = 0;
         uint32_t pphase = 0;
         const int per_img = p.tiles_h * p.tiles_w, half = p.BN >> 1;
@@ -394,6 +400,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
+            if (p.b_resident) continue;
             for (int tap = 0; tap < 9; tap++) {
               mbar_wait(&bars->empty[stage], phase ^ 1u);
               unsigned char *sb = sbst + stage * bstage;
@@ -409,7 +416,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
-          if (p.bias_mma) {
+          if (p.bias_mma && !p.b_resident) {
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             unsigned char *sb = sbst + stage * bstage;
             if (elect_one()) {
@@ -557,6 +564,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sones = smem_u32(smem + p.npatch * kPatchBytes);
         const uint32_t sbst = sones + (p.bias_mma ? (uint32_t)kABytes : 0u);
         if (p.bias_mma) mbar_wait(&bars->ident_full, 0);
+        if (p.b_resident) mbar_wait(&bars->res_full, 0);
         int pb = 0;
         uint32_t pphase = 0;
         for (int tile = w_first; tile < w_total; tile += w_step, it++) {
@@ -564,6 +572,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&bars->tmem_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+          if (p.b_resident) {
+            // weights resident: one patch per 64-channel chunk is all that moves; everything for the tile in one go
+            for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
+              mbar_wait(&bars->patch_full[pb], pphase);
+              tc_fence_after();
+              const uint32_t pbase = smem_u32(smem + pb * kPatchBytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                  const int r = tap / 3, s3 = tap - 3 * r;
+                  const uint32_t off = (uint32_t)(p.tile_t ? s3 * 16 + r : r * 16 + s3) * 128u;
+                  const uint64_t da = make_desc_halo(pbase + off, p.halo_boff);
+                  const uint64_t db = make_desc_kmajor(sbst + (uint32_t)(tap * p.kblocks_per_tap + kc) * b_bytes, 128);
+#pragma unroll
+                  for (int k = 0; k < 4; k++) tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) ? 1u : 0u);
+                }
+                tc_commit(&bars->patch_empty[pb]);
+              }
+              if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
+            }
+            if (elect_one()) {
+              if (p.bias_mma)
+                tc_mma_f16(tmem_d, make_desc_kmajor(sones, 128), make_desc_kmajor(sbst + (uint32_t)(9 * p.kblocks_per_tap) * b_bytes, 128), idesc, 1u);
+              tc_commit(&bars->tmem_full[buf]);
+            }
+            continue;
+          }
           for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
             mbar_wait(&bars->patch_full[pb], pphase);
             tc_fence_after();
@@ -1289,8 +1324,17 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (p.mode == 4) {   // pipeline region: patches | ones tile (bias block) | weight-block stages
     const int bstage = (p.cluster2 == 2 ? BN / 2 : BN) * 128;
     const int fixed = p.bias_mma ? kABytes : 0;
+    static int resident_on = -1;
+    if (resident_on < 0) { const char *e = getenv("ODTK_CONV_RESIDENT_W"); resident_on = e ? atoi(e) : 1; }
+    const int nblocks = 9 * p.kblocks_per_tap + (p.bias_mma ? 1 : 0);
+    if (resident_on && !p.cluster2 && p.num_n_tiles == 1 && 2 * kPatchBytes + fixed + nblocks * bstage <= kPipeBytes) {
+      p.b_resident = 1;
+      p.npatch = (3 * kPatchBytes + fixed + nblocks * bstage <= kPipeBytes) ? 3 : 2;
+      p.nstages = 2;   // unused
+    } else {
     p.npatch = (kPipeBytes - fixed - 3 * kPatchBytes) / bstage >= 6 ? 3 : 2;
     p.nstages = (kPipeBytes - fixed - p.npatch * kPatchBytes) / bstage;
+    }
     if (p.nstages > kMaxStages) p.nstages = kMaxStages;
     if (p.nstages < 2) return ODTK_E_UNSUPPORTED;
   }

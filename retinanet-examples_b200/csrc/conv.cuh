@@ -26,6 +26,7 @@ struct ConvParams {
   int npatch;           // patch buffers (2 or 3); the weight-block stages follow them in the pipeline region
   int tile_t;           // 0: tile = 16 rows x 8 columns of pixels (accumulator row m -> (m / 8, m % 8));
                         // 1: transposed, 8 rows x 16 columns (m -> (m % 8, m / 8)), patch stored column-major
+  int b_resident;       // halo mode: all weight blocks (+ the bias block) fit next to the patches and are loaded once per CTA
   int halo_boff;        // put (start address >> 7) & 7 into the descriptor's base-offset field
   // out_mode ODTK_OUT_CANDIDATES: the decode workspace of this pyramid level (decode.cu)
   int *cand_counts;          // [N]
