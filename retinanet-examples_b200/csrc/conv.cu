@@ -1073,10 +1073,14 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
                  const CUtensorMap &tmO, const CUtensorMap &tmBi, const CUtensorMap &tmR, const CUtensorMap &tmI,
                  const ConvParams &p) {
   const int nchunks = p.BN >> 4;
+  // narrow tiles: 32-column segments (CPW 2) give every epilogue warp ONE segment whose second TMEM load overlaps the
+  // conversion of the first, instead of two serialised 16-column segments (CPW 1)
+  static int cpw1_max = -1;
+  if (cpw1_max < 0) { const char *e = getenv("ODTK_CONV_CPW1_MAX"); cpw1_max = e ? atoi(e) : 2; }
   if (p.cluster2 == 2)   launch_one<4, false, 2>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (p.cluster2)   launch_one<4, false, 1>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (p.upsample)   launch_one<4, true, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (nchunks <= 4) launch_one<1, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (nchunks <= cpw1_max) launch_one<1, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (nchunks <= 8) launch_one<2, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else                   launch_one<4, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
 }

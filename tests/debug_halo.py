@@ -34,7 +34,7 @@ def run(name, n, h, w, cin, cout, mode=0, bias_op=False, residual=False):
         print("   bad h", badh[:24], "bad w", badw[:24], flush=True)
 
 
-print("HALO=%s BOFF=%s" % (os.environ.get("ODTK_CONV_HALO", "1"), os.environ.get("ODTK_CONV_HALO_BOFF", "1")))
+print("HALO=%s BOFF=%s" % (os.environ.get("ODTK_CONV_HALO", "1"), os.environ.get("ODTK_CONV_HALO_BOFF", "0")))
 run("64->64 16x8 one tile", 1, 16, 8, 64, 64)
 run("64->64 32x24", 1, 32, 24, 64, 64)
 run("64->64 40x64 (transposed)", 1, 40, 64, 64, 64)
