@@ -210,6 +210,14 @@ class FullWorkload:
                 "detections_in_last_step": n_det,
                 "l2": "activations of a step (GBs) exceed the 126 MB L2; input batch %.0f MB" % (self.h2d_bytes / 1e6)}
 
+    def _profiled_traffic(self):
+        if not (self.backbone == "ResNet50FPN" and self.batch == 32 and not self.rotated):
+            return None
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", "r01_layer_table.json")))["summary"]["conv_dram_bytes"])
+        except (OSError, KeyError, ValueError):
+            return None
+
     def roofline(self, lib, peaks, steps):
         ms, n = _prof_get(lib, 3)
         if n == 0:
@@ -229,10 +237,10 @@ class FullWorkload:
                                   "the bound of layer-by-layer execution; frac_of_step = ideal / measured ms_per_step"}
         return {"kernel": "conv_gemm_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum summed over the 111 conv launches of ONE step
-                # (profiles/r01_conv_step_dram.csv, ncu capture of this command at ResNet50FPN batch 32)
-                "traffic": 45850652672 if (self.backbone == "ResNet50FPN" and self.batch == 32 and not self.rotated) else None,
-                "traffic_note": "bytes per step (all conv launches), from profiles/r01_conv_step_dram_summary.json",
+                # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the
+                # committed ncu capture of this workload (tools/capture_step.py -> profiles/r01_layer_table.json)
+                "traffic": self._profiled_traffic(),
+                "traffic_note": "bytes per step (all conv launches), from profiles/r01_layer_table.json (ncu, same workload)",
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "avg_launch_ms": round(ms / n, 5), "launches_timed": n,
                 "algorithmic_flops_per_step": int(self.flops_per_step),
