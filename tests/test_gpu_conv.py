@@ -161,3 +161,44 @@ def test_cluster_multicast_path(n, h, w, cin, cout, ks):
     else:
         y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=True, bias_op=engine.pack_bias(bd))
         _close16(y, _ref_conv(x, wt, b, ks, relu=True))
+
+
+# ---- halo mode (3x3 stride 1: one patch load per 64-channel chunk, nine shifted UMMA views) ---------------------------
+# shapes chosen to hit: a single 16x8 tile, ragged right/bottom edges, the transposed 8x16 tiling (W multiple of 16,
+# H not of 16), two channel chunks, 2-CTA pairs (256-wide, >= 74 tile pairs) with the bias K block, several N tiles,
+# resident weights (64 -> 64) with and without a residual, and the fp32 NCHW head outputs.
+@pytest.mark.parametrize("n,h,w,cin,cout,bias_op,residual,relu", [
+    (1, 16, 8, 64, 64, False, False, False), (1, 32, 24, 64, 64, True, False, True), (1, 40, 64, 64, 64, True, True, True),
+    (2, 33, 47, 128, 128, False, False, True), (4, 48, 64, 256, 256, True, False, True), (1, 104, 160, 256, 256, True, False, False),
+    (1, 9, 17, 64, 128, True, False, False), (2, 24, 16, 256, 512, True, False, True), (1, 8, 8, 128, 64, False, True, False)])
+def test_conv3x3_halo_mode_matches_torch(n, h, w, cin, cout, bias_op, residual, relu):
+    g = torch.Generator().manual_seed(h * 131 + w * 7 + cin + cout)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 3, 3), g, 0.03), torch.randn(cout, generator=g)
+    res = _rand((n, h, w, cout), g) if residual else None
+    bop = engine.pack_bias(b.to(DEV)) if bias_op else None
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 3, relu=relu,
+                      residual=res.to(DEV) if residual else None, bias_op=bop)
+    _close16(y, _ref_conv(x, wt, b, 3, relu=relu, residual=res))
+
+
+@pytest.mark.parametrize("n,h,w,cout,mode", [(1, 48, 40, 36, engine.OUT_NCHW_F32), (2, 32, 40, 720, engine.OUT_NCHW_F32_SIGMOID),
+                                            (1, 100, 160, 36, engine.OUT_NCHW_F32), (1, 25, 40, 720, engine.OUT_NCHW_F32)])
+def test_conv3x3_halo_mode_head_outputs(n, h, w, cout, mode):
+    g = torch.Generator().manual_seed(h + w + cout)
+    x, wt, b = _rand((n, h, w, 256), g), _rand((cout, 256, 3, 3), g, 0.02), torch.randn(cout, generator=g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 3, out_mode=mode,
+                      bias_op=engine.pack_bias(b.to(DEV)))
+    ref = _ref_conv(x, wt, b, 3)
+    if mode == engine.OUT_NCHW_F32_SIGMOID:
+        ref = torch.sigmoid(ref)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 32, 16), (2, 34, 50), (1, 800, 1280)])
+def test_stem_raw_window_mode_edges(n, h, w):
+    """Raw-window stem on sizes whose 16x8 output tiles are ragged, and on the benchmark's full size."""
+    g = torch.Generator().manual_seed(h * 3 + w)
+    x, wt, b = _rand((n, h, w, 3), g), _rand((64, 3, 7, 7), g, 0.1), torch.randn(64, generator=g)
+    y = engine.stem_conv(x.to(DEV), engine.pack_stem_weight(wt.float()).to(DEV), b.to(DEV), 64, relu=True)
+    _close16(y, _ref_conv(x, wt, b, 7, relu=True, stride=2, pad=3))
