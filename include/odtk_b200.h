@@ -208,6 +208,23 @@ long long odtk_smooth_l1_loss(const float *pred, const float *target, const floa
                               float beta, float grad_scale, float *loss_elem, float *loss_sum, float *grad,
                               void *workspace, size_t workspace_size, odtk_stream_t stream);
 
+/* ---- anchor target assignment --------------------------------------------
+ * Replaces snap_to_anchors (odtk/box.py:134-186) + box2delta (:67-78) as called per image and level by
+ * Model._extract_targets (odtk/model.py:167-184), for the whole batch in one launch.
+ *   targets [B, G, 5] fp32 device: x, y, w, h, class; rows with class <= -1 are padding (the reference
+ *   filters them on the host, odtk/model.py:174).  anchors: HOST pointer, 4*A floats (generate_anchors).
+ *   Grid position (y, x) of anchor a covers (x*stride, y*stride) + anchors[a].
+ * Outputs (device, fp32 unless noted), in the reference's layouts:
+ *   cls_target [B, A, C, H, W] dense one-hot, may be NULL;  box_target [B, A, 4, H, W];
+ *   depth [B, A, 1, H, W]: -1 ignored (iou_bg <= IoU < iou_fg), 0 background, class + 1 foreground;
+ *   cls_index [B, A, H, W] int32, may be NULL: class, -1 background, -2 ignored -- the class-index
+ *   target layout odtk_focal_loss consumes (B200-native: the dense one-hot never has to exist).
+ * An image without valid rows yields zeros everywhere (odtk/box.py:140-143) and cls_index -1.         */
+int odtk_snap_to_anchors(const float *targets, int batch, int max_boxes, int height, int width, int stride,
+                         const float *anchors, int num_anchors, int num_classes, float iou_bg, float iou_fg,
+                         float *cls_target, float *box_target, float *depth, int *cls_index,
+                         odtk_stream_t stream);
+
 /* ---- input side of `odtk infer` ---------------------------------------
  * Replaces the per-image tensor maths of CocoDataset.__getitem__ (odtk/data.py:113-123): uint8 HWC
  * [n,h,w,3] -> /255 -> (x - mean)/std -> zero padding to [hs, ws] (a multiple of the model stride),

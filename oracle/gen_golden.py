@@ -12,6 +12,7 @@ What each fixture is (reference function -> file):
   decode.npz       odtk.box.decode CPU path (odtk/box.py:266-309) with '/' -> '//' on the three
                    index divisions that crash on torch >= 1.6 (ref_import.patched_cpu_decode)
   focal.npz        odtk.loss.FocalLoss forward + autograd backward (odtk/loss.py:13-18)
+  snap.npz         odtk.box.snap_to_anchors (odtk/box.py:134-186), unmodified, CPU
   model_*.npz      odtk.model.Model forward (exporting=True head outputs, and the full inference
                    branch with the patched CPU decode + unmodified CPU nms)
 """
@@ -119,14 +120,49 @@ def gen_focal(odtk):
                         grad=xt.grad.numpy())
 
 
+def gen_snap(odtk):
+    """odtk.box.snap_to_anchors (odtk/box.py:134-186), unmodified, on CPU: seeded ground-truth boxes over small
+    grids, incl. an image without boxes and boxes that exactly tile anchors (IoU ties / thresholds)."""
+    rng = np.random.default_rng(77)
+    ratios, scales = [1.0, 2.0, 0.5], [4 * 2 ** (i / 3) for i in range(3)]
+    d = {}
+    cases = [(12, 9, 8, 7, 5), (10, 16, 16, 12, 3), (5, 4, 32, 0, 4), (7, 6, 64, 300, 6), (16, 10, 8, 20, 80)]   # W, H, stride, #gt, classes
+    for k, (w, h, stride, g, ncls) in enumerate(cases):
+        anchors = odtk.box.generate_anchors(stride, ratios, scales)
+        size = [w * stride, h * stride]
+        if g:
+            wh = rng.uniform(0.5 * stride, 12.0 * stride, size=(g, 2))
+            xy = rng.uniform(-stride, [size[0], size[1]], size=(g, 2)) - wh / 4
+            cls = rng.integers(0, ncls, size=(g, 1))
+            boxes = np.concatenate([np.round(xy), np.round(wh) + 1, cls], 1).astype(np.float32)
+            if g >= 5:      # boxes coinciding with anchors of some cells -> IoU exactly 1 and exact ties
+                a = anchors.numpy()
+                for j in range(3):
+                    cx, cy = int(rng.integers(0, w)) * stride, int(rng.integers(0, h)) * stride
+                    an = a[int(rng.integers(0, a.shape[0]))]
+                    boxes[j, :4] = [cx + an[0], cy + an[1], an[2] - an[0] + 1, an[3] - an[1] + 1]
+                boxes[4] = boxes[3]          # duplicate row: first maximum must win
+                boxes[4, 4] = (boxes[3, 4] + 1) % ncls
+        else:
+            boxes = np.zeros((0, 5), np.float32)
+        ct, bt, dp = odtk.box.snap_to_anchors(torch.from_numpy(boxes), size, stride, anchors, ncls, "cpu", [0.4, 0.5])
+        d.update({"c%d_boxes" % k: boxes, "c%d_size" % k: np.int32(size), "c%d_stride" % k: np.int32(stride),
+                  "c%d_anchors" % k: anchors.numpy(), "c%d_classes" % k: np.int32(ncls),
+                  "c%d_cls_target" % k: ct.numpy().astype(np.uint8), "c%d_box_target" % k: bt.numpy(),
+                  "c%d_depth" % k: dp.numpy()})
+    d["ncases"] = np.int32(len(cases))
+    np.savez_compressed(os.path.join(OUT, "snap.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     odtk = ref_import.import_reference()
-    which = sys.argv[1:] or ["anchors", "nms", "decode", "focal", "model"]
+    which = sys.argv[1:] or ["anchors", "nms", "decode", "focal", "snap", "model"]
     if "anchors" in which: gen_anchors(odtk)
     if "nms" in which: gen_nms(odtk)
     if "decode" in which: gen_decode(odtk)
     if "focal" in which: gen_focal(odtk)
+    if "snap" in which: gen_snap(odtk)
     if "model" in which:
         from oracle import gen_golden_model
         gen_golden_model.main(odtk, OUT)

@@ -164,3 +164,52 @@ def preprocess_u8(image, stride=128, mean=(0.485, 0.456, 0.406), std=(0.229, 0.2
     out = np.empty((3, hs, ws), np.float32)
     lib().oracle_preprocess_u8(img.ctypes.data_as(ctypes.c_void_p), h, w, hs, ws, _p(_f32(mean)), _p(_f32(std)), _p(out))
     return out
+
+
+def snap_to_anchors(boxes, size, stride, anchors, num_classes, anchor_ious):
+    """Restatement of odtk/box.py:134-186 (snap_to_anchors) + :67-78 (box2delta) in numpy fp32, same operation
+    order.  boxes [G, 5] (x, y, w, h, class) of one image, size = [W*stride, H*stride], anchors [A, 4].
+    Returns (cls_target [A,C,H,W], box_target [A,4,H,W], depth [A,1,H,W], cls_index [A,H,W] int32), the last
+    being the class-index form (class, -1 background, -2 ignored) of the same assignment."""
+    f = np.float32
+    anchors = np.asarray(anchors, dtype=f).reshape(-1, 4)
+    A = anchors.shape[0]
+    width, height = int(size[0] / stride), int(size[1] / stride)
+    boxes = np.asarray(boxes, dtype=f).reshape(-1, 5)
+    boxes = boxes[boxes[:, 4] > -1]                                   # odtk/model.py:174
+    if boxes.size == 0:                                               # :140-143
+        return (np.zeros((A, num_classes, height, width), f), np.zeros((A, 4, height, width), f),
+                np.zeros((A, 1, height, width), f), np.full((A, height, width), -1, np.int32))
+    classes = boxes[:, 4]
+    xs, ys = np.arange(0, size[0], stride, dtype=f), np.arange(0, size[1], stride, dtype=f)
+    x, y = np.meshgrid(xs, ys, indexing="ij")                         # [W, H] (torch.meshgrid default)
+    xyxy = np.stack((x, y, x, y), 2)[None]
+    anc = (xyxy + anchors.reshape(-1, 1, 1, 4)).astype(f).reshape(-1, 4)
+    b = np.concatenate([boxes[:, :2], boxes[:, :2] + boxes[:, 2:4] - f(1)], 1).astype(f)
+    d = np.clip(np.minimum(anc[:, None, 2:], b[:, 2:]) - np.maximum(anc[:, None, :2], b[:, :2]) + f(1), 0, None)
+    inter = d[..., 0] * d[..., 1]
+    b_area = (b[:, 2] - b[:, 0] + f(1)) * (b[:, 3] - b[:, 1] + f(1))
+    a_area = (anc[:, 2] - anc[:, 0] + f(1)) * (anc[:, 3] - anc[:, 1] + f(1))
+    overlap = inter / (a_area[:, None] + b_area - inter)
+    idx = overlap.argmax(1)                                           # first maximum, like torch.max
+    ov = overlap[np.arange(overlap.shape[0]), idx]
+    bb = b[idx]
+    a_wh = anc[:, 2:] - anc[:, :2] + f(1)                             # box2delta
+    a_ctr = anc[:, :2] + f(0.5) * a_wh
+    b_wh = bb[:, 2:] - bb[:, :2] + f(1)
+    b_ctr = bb[:, :2] + f(0.5) * b_wh
+    delta = np.concatenate([(b_ctr - a_ctr) / a_wh, np.log(b_wh / a_wh)], 1).astype(f)
+    box_target = delta.reshape(A, width, height, 4).transpose(0, 3, 2, 1)
+    depth = np.full(ov.shape, -1, f)
+    depth[ov < f(anchor_ious[0])] = 0
+    fg = ov >= f(anchor_ious[1])
+    depth[fg] = classes[idx][fg] + f(1)
+    cls = classes[idx].astype(np.int64)
+    onehot = np.where(ov < f(anchor_ious[0]), num_classes, cls)
+    cls_target = np.zeros((anc.shape[0], num_classes + 1), f)
+    cls_target[np.arange(anc.shape[0]), onehot] = 1
+    cls_target = cls_target[:, :num_classes].reshape(A, width, height, num_classes).transpose(0, 3, 2, 1)
+    cls_index = np.where(ov < f(anchor_ious[0]), -1, np.where(fg, cls, -2)).astype(np.int32)
+    return (np.ascontiguousarray(cls_target), np.ascontiguousarray(box_target),
+            np.ascontiguousarray(depth.reshape(A, width, height).transpose(0, 2, 1))[:, None],
+            np.ascontiguousarray(cls_index.reshape(A, width, height).transpose(0, 2, 1)))

@@ -96,3 +96,42 @@ def nms_rotated(all_scores, all_boxes, all_classes, nms=0.5, ndetections=100):
 DEFAULT_RATIOS = [1.0, 2.0, 0.5]
 DEFAULT_SCALES = [4 * 2 ** (i / 3) for i in range(3)]
 DEFAULT_ANGLES = [-math.pi / 6, 0, math.pi / 6]
+
+
+def snap_to_anchors_batch(targets, size, stride, anchors, num_classes, anchor_ious, dense=True):
+    """Target assignment for a whole batch at one pyramid level in ONE launch (odtk_snap_to_anchors).
+    targets [B, G, 5] fp32 CUDA (x, y, w, h, class; class <= -1 = padding row, skipped on the device);
+    size = (H, W) of the head tensors; anchors [A, 4].  Returns (cls_target [B,A,C,H,W] or None when
+    dense=False, box_target [B,A,4,H,W], depth [B,A,1,H,W], cls_index [B,A,H,W] int32) -- the stacked results of
+    Model._extract_targets (odtk/model.py:167-184) plus the class-index targets loss.FocalLoss accepts."""
+    import ctypes
+    from . import _lib
+    if not (targets.is_cuda and targets.dtype == torch.float32 and targets.dim() == 3 and targets.size(2) == 5):
+        raise ValueError("targets must be a CUDA fp32 [B, G, 5] tensor: there is no CPU path")
+    targets = targets.contiguous()
+    batch, g = targets.size(0), targets.size(1)
+    h, w = int(size[0]), int(size[1])
+    a = anchors.reshape(-1, 4)
+    na, dev = a.size(0), targets.device
+    host = (ctypes.c_float * (4 * na))(*[float(v) for v in a.reshape(-1).tolist()])
+    cls_target = torch.empty((batch, na, num_classes, h, w), dtype=torch.float32, device=dev) if dense else None
+    box_target = torch.empty((batch, na, 4, h, w), dtype=torch.float32, device=dev)
+    depth = torch.empty((batch, na, 1, h, w), dtype=torch.float32, device=dev)
+    cls_index = torch.empty((batch, na, h, w), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().odtk_snap_to_anchors(
+        ctypes.c_void_p(targets.data_ptr()) if g else None, batch, g, h, w, int(stride),
+        ctypes.cast(host, ctypes.POINTER(ctypes.c_float)), na, int(num_classes), float(anchor_ious[0]), float(anchor_ious[1]),
+        ctypes.c_void_p(cls_target.data_ptr()) if dense else None, ctypes.c_void_p(box_target.data_ptr()),
+        ctypes.c_void_p(depth.data_ptr()), ctypes.c_void_p(cls_index.data_ptr()),
+        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "snap_to_anchors")
+    return cls_target, box_target, depth, cls_index
+
+
+def snap_to_anchors(boxes, size, stride, anchors, num_classes, device, anchor_ious):
+    """'Snap target boxes (x, y, w, h) to anchors' -- odtk/box.py:134-186, same signature and results:
+    boxes [G, 5] (x, y, w, h, class) of ONE image, size = [W*stride, H*stride]; returns
+    (cls_target [A,C,H,W], box_target [A,4,H,W], depth [A,1,H,W])."""
+    width, height = int(size[0] / stride), int(size[1] / stride)
+    t = boxes.to(device=device, dtype=torch.float32).reshape(1, -1, 5)
+    cls_target, box_target, depth, _ = snap_to_anchors_batch(t, (height, width), stride, anchors, num_classes, anchor_ious)
+    return cls_target[0], box_target[0], depth[0]

@@ -139,3 +139,20 @@ def test_l1_and_preprocess_oracle_match_reference(golden_dir):
     np.testing.assert_allclose(gr.reshape(g["grad"].shape), g["grad"], rtol=1e-5, atol=1e-6)
     pre = oracle.preprocess_u8(g["img"])
     np.testing.assert_allclose(pre, g["pre"], rtol=1e-6, atol=1e-6)
+
+
+def test_snap_to_anchors_oracle_matches_reference(golden_dir):
+    """oracle.snap_to_anchors vs odtk.box.snap_to_anchors run unmodified on CPU (tests/golden/snap.npz): depth and
+    one-hot classes bit-exact (IoU thresholds, first-maximum ties, the empty image), box deltas to 1e-6 (log)."""
+    g = np.load(os.path.join(golden_dir, "snap.npz"))
+    for k in range(int(g["ncases"])):
+        ct, bt, dp, ci = oracle.snap_to_anchors(g["c%d_boxes" % k], g["c%d_size" % k].tolist(), int(g["c%d_stride" % k]),
+                                                g["c%d_anchors" % k], int(g["c%d_classes" % k]), [0.4, 0.5])
+        np.testing.assert_array_equal(dp, g["c%d_depth" % k])
+        np.testing.assert_array_equal(ct.astype(np.uint8), g["c%d_cls_target" % k])
+        np.testing.assert_allclose(bt, g["c%d_box_target" % k], rtol=1e-6, atol=1e-6)
+        # the class-index form is the same assignment: foreground <=> depth > 0, ignored <=> depth == -1
+        d = dp[:, 0]
+        np.testing.assert_array_equal(ci >= 0, d > 0)
+        np.testing.assert_array_equal(ci == -2, d == -1)
+        np.testing.assert_array_equal(ci[ci >= 0], d[d > 0].astype(np.int32) - 1)
