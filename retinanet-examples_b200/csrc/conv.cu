@@ -6,23 +6,34 @@
 //
 //   D[pixels, Cout] = sum over taps (r,s) and 64-channel chunks of  A_tap[pixels, 64] * W[Cout, 64]^T
 //
-//   warp 0   TMA producer: for every (tap, chunk) one cp.async.bulk.tensor load of the SHIFTED
-//            activation patch straight from the NHWC tensor (4-D tensor map, box = 64 ch x TW x TH;
-//            the hardware zero-fills out-of-bounds rows/columns == conv padding, so no im2col and
-//            no border code) and one of the weight tile (2-D map over [Cout, taps*Cin]); both land
-//            in 128-byte-swizzled shared memory stages guarded by full/empty mbarriers.
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N<=256,
-//            K=16) x4 per stage, fp32 accumulation in TMEM; tcgen05.commit releases the stage and,
-//            after the last K block, hands the accumulator to the epilogue.
+//   warp 0   TMA producer (converged warp, one elect.sync lane issues): cp.async.bulk.tensor loads of the
+//            activation operand straight from the NHWC tensor (the hardware zero-fills out-of-bounds
+//            rows/columns == conv padding: no im2col, no border code) and of the weight blocks (2-D map
+//            over [Cout, taps*Cin]) into swizzled shared memory guarded by full/empty mbarriers.
+//   warp 1   MMA issuer (converged warp, one elect.sync lane issues): tcgen05.mma kind::f16, M = 128
+//            (cta_group::1) or 256 across a CTA pair (cta_group::2), N <= 256, K = 16, fp32 accumulation
+//            in TMEM; tcgen05.commit releases the stage and, after the last K block, hands the
+//            accumulator to the epilogue.  Bias = one extra K block (A = ones); bottleneck residual =
+//            D += I * R with the residual tile as an MN-major B operand.
 //   warp 2   TMEM allocator (512 columns = two accumulator buffers, so the epilogue of tile i
 //            overlaps the MMAs of tile i+1).
-//   warps 4-7 epilogue: tcgen05.ld the accumulator (one output pixel per thread), fused
-//            bias (folded BatchNorm) + residual add + FPN nearest-upsample add + ReLU, fp16 NHWC
-//            store -- or, for the last convolution of a head, (sigmoid +) fp32 NCHW store in the
-//            layout the reference's decode entry point expects.
+//   warps 4-11 epilogue: tcgen05.ld the accumulator (one output pixel per thread), FPN nearest-upsample
+//            add + ReLU, fp16 NHWC store (TMA bulk store for the wide 1x1 layers) -- or, for the last
+//            convolution of a head, (sigmoid +) fp32 NCHW store in the layout the reference's decode entry
+//            point expects -- or, class head on the inference path, sigmoid + threshold + candidate append
+//            straight into the decode workspace (ODTK_OUT_CANDIDATES).
 //
-// 1x1 convolutions use the same kernel with a 2-D [pixels, Cin] map (plain GEMM rows).
-// Strided and 7x7 convolutions are lowered by layers.cu to one of the two forms.
+// A-operand modes (ConvParams::mode):
+//   0  1x1: 2-D [pixels, Cin] map (plain GEMM rows).
+//   4  3x3 stride 1, "halo": the input patch of a 16x8 / 8x16 pixel tile is loaded ONCE per 64-channel
+//      chunk ([18][16-pixel pitch][64 ch], one 4-D box) and the nine taps are nine shifted UMMA views of
+//      it (make_desc_halo); weights stream behind it, or stay resident when they all fit.
+//   1  3x3 stride 1, one SHIFTED 4-D box per tap (fallback for shapes the fixed halo tiles fit badly).
+//   3  stride-2 1x1 / 3x3 on even sizes: parity-split 5-D view {2C, W/2, 2, H/2, N}.
+//   5  7x7 stride-2 stem, "raw window": the zero-padded NHWC4 image patch is read by the tensor core as an
+//      un-swizzled K-major operand whose 16-byte row pitch is the distance between neighbouring windows
+//      (make_desc_raw); weights resident.   2 = the older overlapping-window 5-D TMA map (fallback).
+// Odd-sized strided convolutions are first lowered to GEMM rows by layers.cu and run as mode 0.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
