@@ -452,8 +452,13 @@ def main():
         ms_prof, _, _ = timed(getattr(wl, "step_profile", wl.step), args.steps, profile=True)
         roof = wl.roofline(lib, peaks, args.steps)
         if roof is not None and "conv_share_of_step" in roof:
+            # share of the step's summed KERNEL time (every launch of the eager, single-stream step is bracketed by
+            # events: decode 0-1, nms 2, conv 3, pad / max-pool / lowering 5) -- comparable with the ncu launch list
             cms, _ = _prof_get(lib, 3)
-            roof["conv_share_of_step"] = round(cms / ms_prof, 4)
+            kernel_ms = sum(_prof_get(lib, t)[0] for t in (0, 1, 2, 3, 5))
+            roof["conv_share_of_step"] = round(cms / kernel_ms, 4)
+            roof["kernel_ms_per_step"] = round(kernel_ms / args.steps, 4)
+            roof["eager_ms_per_step"] = round(ms_prof / args.steps, 4)
         if roof is not None and getattr(wl, "layerwise", None):
             wl.layerwise["frac_of_step"] = round(wl.layerwise["ideal_ms_per_step"] / (ms / args.steps), 4)
             roof["layerwise"] = wl.layerwise

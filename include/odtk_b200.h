@@ -236,7 +236,8 @@ int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, int hs, int 
 /* ---- per-kernel timing (B200-native addition; the reference has only a wall-clock
  * Profiler without CUDA sync, odtk/utils.py:140-167) ------------------------------
  * When enabled, every launch of a tagged kernel is bracketed by CUDA events on the
- * launching stream.  Tags: 0 score filter, 1 select+decode, 2 nms, 3 conv, 4 loss.
+ * launching stream.  Tags: 0 score filter, 1 select+decode, 2 nms, 3 conv, 4 loss / target
+ * assignment, 5 pad / max-pool / lowering / preprocess.
  * odtk_prof_get synchronises the device and returns summed ms and launch count.  */
 void odtk_prof_enable(int on);
 void odtk_prof_reset(void);

@@ -164,13 +164,14 @@ extern "C" int odtk_lower_conv(const void *x, void *out, int n, int h, int w, in
   if (kpad < ksize * ksize * c || (kpad % 8)) return ODTK_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+  if (c % 8 == 0 && kpad != ksize * ksize * c) return ODTK_E_INVALID;
+  if (c % 8 != 0 && relu) return ODTK_E_UNSUPPORTED;
+  OdtkProfScope prof(ODTK_PROF_LAYER, stream);
   if (c % 8 == 0) {
-    if (kpad != ksize * ksize * c) return ODTK_E_INVALID;
     long long total = (long long)n * oh * ow * ksize * ksize * (c / 8);
     lower_vec8_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half *)x, (__half *)out, n, h, w, c, oh, ow,
                                                                 ksize, stride, pad, kpad, relu);
   } else {
-    if (relu) return ODTK_E_UNSUPPORTED;
     long long total = (long long)n * oh * ow * (kpad / 8);
     lower_generic_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half *)x, (__half *)out, n, h, w, c, oh,
                                                                    ow, ksize, stride, pad, kpad);
@@ -182,6 +183,7 @@ extern "C" int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, in
   if (!x || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return ODTK_E_INVALID;
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
   long long total = (long long)n * oh * ow * (c / 8);
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w,
                                                                                c, oh, ow);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
@@ -190,6 +192,7 @@ extern "C" int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, in
 extern "C" int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_stream_t stream_) {
   if (!x || !y || n <= 0 || h <= 0 || w <= 0) return ODTK_E_INVALID;
   long long total = (long long)n * (h + 6) * (w + 8);
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
   pad_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
@@ -198,6 +201,7 @@ extern "C" int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, i
                                   const float *std, odtk_stream_t stream_) {
   if (!x || !y || !mean || !std || n <= 0 || h <= 0 || w <= 0 || hs < h || ws < w) return ODTK_E_INVALID;
   long long total = (long long)n * (hs + 6) * (ws + 8);
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
   preprocess_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
       (const unsigned char *)x, (__half *)y, n, h, w, hs, ws, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;

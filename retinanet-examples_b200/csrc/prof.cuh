@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 
 enum OdtkProfTag { ODTK_PROF_FILTER = 0, ODTK_PROF_SELECT = 1, ODTK_PROF_NMS = 2, ODTK_PROF_CONV = 3,
-                   ODTK_PROF_LOSS = 4, ODTK_PROF_NTAGS = 8 };
+                   ODTK_PROF_LOSS = 4, ODTK_PROF_LAYER = 5 /* pad, max-pool, lowering, preprocess */, ODTK_PROF_NTAGS = 8 };
 
 void odtk_prof_begin(int tag, cudaStream_t s);
 void odtk_prof_end(int tag, cudaStream_t s);
