@@ -170,6 +170,16 @@ typedef struct {
   const odtk_cand_sink_t *sink; /* out_mode ODTK_OUT_CANDIDATES: where the candidates go (host struct)       */
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
+/* Introspection (tests): the kernel variant the last odtk_conv2d / odtk_stem_conv call of the calling host thread
+ * launched.  mode: 0 GEMM rows (1x1), 1 shifted box per tap, 3 stride 2, 4 halo (3x3 s1), 5 raw-window stem;
+ * cluster: 0 single CTAs, 1 2-CTA multicast pairs, 2 cta_group::2 pairs.                                    */
+typedef struct {
+  int mode, cluster, bn, num_m_tiles, num_n_tiles, nstages, npatch, tile_t, b_resident, bias_mma, res_mma, tma_store;
+  int th, tw, grid, up_mma;
+} odtk_conv_plan_t;
+int odtk_conv_last_plan(odtk_conv_plan_t *out);
+/* Encoded tensor maps are cached per (base pointer, geometry); hit / miss counters of the process.         */
+int odtk_conv_map_cache_stats(long long *hits, long long *misses);
 /* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */
 int odtk_conv_pack_bias(const float *bias, void *out, int cout, odtk_stream_t stream);
 

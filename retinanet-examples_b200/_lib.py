@@ -46,6 +46,8 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "odtk_conv_last_plan": (ctypes.c_int, [ctypes.c_void_p]),
+    "odtk_conv_map_cache_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
     "odtk_conv_pack_bias": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "odtk_lower_conv": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_void_p]),
     "odtk_maxpool3x3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]),
@@ -70,6 +72,13 @@ class Level(ctypes.Structure):
     """odtk_level_t (include/odtk_b200.h)."""
     _fields_ = [("scores", ctypes.c_void_p), ("deltas", ctypes.c_void_p), ("height", ctypes.c_size_t),
                 ("width", ctypes.c_size_t), ("scale", ctypes.c_size_t), ("anchors", _c_f32p)]
+
+
+class ConvPlan(ctypes.Structure):
+    """odtk_conv_plan_t (include/odtk_b200.h)."""
+    _fields_ = [(n, ctypes.c_int) for n in ("mode", "cluster", "bn", "num_m_tiles", "num_n_tiles", "nstages", "npatch",
+                                            "tile_t", "b_resident", "bias_mma", "res_mma", "tma_store", "th", "tw", "grid",
+                                            "up_mma")]
 
 
 class CandSink(ctypes.Structure):

@@ -9,6 +9,17 @@
 
 static inline size_t odtk_align_up(size_t x) { return (x + ODTK_ALIGN - 1) / ODTK_ALIGN * ODTK_ALIGN; }
 
+// SM count of the CURRENT device (cached per device ordinal; grids are sized from it, never from a constant)
+static inline int odtk_sm_count() {
+  static int cache[64];
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
 // Monotone float -> uint32 key; larger key == larger float.  This is the transform
 // cub::DeviceRadixSort applies to float keys, so "descending, stable" in the
 // reference (decode.cu:111, nms.cu:135) == descending on (key, ~position).

@@ -38,6 +38,10 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "conv.cuh"
@@ -88,6 +92,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
@@ -364,7 +374,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kStemPatchBytes);
-            tma_load_4d(smem + stage * kStemPatchSlot, &tmA, &bars->full[stage], 0, w0, 2 * h0, img);
+            // patch rows as whole 192-byte runs of the padded image row (3-D map); the older 4-D map fetched the same
+            // bytes as 12 separate 16-byte pixel pairs per row (444 TMA rows per tile: request-bound)
+            if (p.stem_rows) tma_load_3d(smem + stage * kStemPatchSlot, &tmA, &bars->full[stage], 8 * w0, 2 * h0, img);
+            else             tma_load_4d(smem + stage * kStemPatchSlot, &tmA, &bars->full[stage], 0, w0, 2 * h0, img);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -1021,18 +1034,54 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Encoded descriptors are pure functions of (base, geometry): cache them, so that eager / batch-1 callers stop paying
+// 3-7 driver encodes per convolution (a CUDA-graph replay never did).  Keyed by value; bounded; thread-safe.
+struct MapKey {
+  const void *base;
+  int rank, swz;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], es[5];
+  bool operator==(const MapKey &o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey &k) const {
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey); i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+long long g_map_hits = 0, g_map_misses = 0;
+
 bool encode_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                const uint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                const uint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, const uint32_t *elem_strides = nullptr) {
+  MapKey key;
+  memset(&key, 0, sizeof key);
+  key.base = base; key.rank = rank; key.swz = (int)swz;
+  for (int i = 0; i < rank; i++) { key.dims[i] = dims[i]; key.box[i] = box[i]; key.es[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i < rank - 1; i++) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *m = it->second; g_map_hits++; return true; }
+  }
   EncodeTiledFn fn = get_encode();
   if (!fn) return false;
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = key.es[i]; }
   for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_map_cache.size() >= 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, *m);
+  g_map_misses++;
+  return true;
 }
 
 // pick the spatial patch (TW x TH <= 128 pixels) that wastes the fewest accumulator rows
@@ -1050,8 +1099,6 @@ void choose_patch(int H, int W, int &TH, int &TW) {
     }
   }
 }
-
-int g_num_sms = 0;
 
 template <int CPW, bool UPS, int CL2>
 bool configure_one() {
@@ -1096,23 +1143,12 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
   else                   launch_one<4, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
 }
 
-// constant A operand of the residual MMAs: the 128 x 128 identity
+// constant operands: the 128 x 128 identity (A operand of the residual MMAs) and the ones tile (A operand of the bias
+// block: 128 rows x 64 fp16, columns 0 and 1 are 1.0).  __device__ globals: one instance per device.
 __device__ __half g_ident_op[128 * 128];
-__global__ void init_ident_kernel() {
-  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) g_ident_op[i] = __float2half_rn((i >> 7) == (i & 127) ? 1.0f : 0.0f);
-}
-const void *ident_operand(cudaStream_t stream) {
-  static void *ptr = nullptr;
-  if (!ptr) {
-    if (cudaGetSymbolAddress(&ptr, g_ident_op) != cudaSuccess) return nullptr;
-    init_ident_kernel<<<1, 256, 0, stream>>>();
-  }
-  return ptr;
-}
-
-// constant A operand of the bias block: 128 rows x 64 fp16, columns 0 and 1 are 1.0
 __device__ __half g_ones_op[128 * 64];
-__global__ void init_ones_kernel() {
+__global__ void init_const_operands_kernel() {
+  for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) g_ident_op[i] = __float2half_rn((i >> 7) == (i & 127) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_ones_op[i] = __float2half_rn((i & 63) < 2 ? 1.0f : 0.0f);
 }
 // bias operand: [cout, 64] fp16 with (hi, lo, 0, ...): hi + lo == bias to 2^-22 relative
@@ -1128,14 +1164,40 @@ __global__ void pack_bias_kernel(const float *bias, __half *out, int cout) {
     out[i] = __float2half_rn(v);
   }
 }
-const void *ones_operand(cudaStream_t stream) {
-  static void *ptr = nullptr;
-  if (!ptr) {
-    if (cudaGetSymbolAddress(&ptr, g_ones_op) != cudaSuccess) return nullptr;
-    init_ones_kernel<<<1, 256, 0, stream>>>();
+
+// Per-device state (one process may drive several GPUs): SM count, the > 48 KB dynamic-shared-memory opt-in of every
+// kernel instance (a per-device function attribute) and the addresses of the constant operands, initialised once per
+// device.  The init kernel runs on the caller's stream and is followed by a device-wide synchronisation unless that
+// stream is capturing (then it simply becomes part of the graph), so later callers on OTHER streams are ordered too.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  bool ready;
+  int num_sms;
+  void *ident, *ones;
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+
+const DeviceState *device_state(cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceState &d = g_dev[dev];
+  if (d.ready) return &d;
+  if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.num_sms <= 0) return nullptr;
+  if (!configure_kernels()) return nullptr;
+  if (cudaGetSymbolAddress(&d.ident, g_ident_op) != cudaSuccess || cudaGetSymbolAddress(&d.ones, g_ones_op) != cudaSuccess) return nullptr;
+  init_const_operands_kernel<<<1, 256, 0, stream>>>();
+  if (cudaGetLastError() != cudaSuccess) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
   }
-  return ptr;
+  d.ready = true;
+  return &d;
 }
+
+thread_local odtk_conv_plan_t g_last_plan;
 
 }  // namespace
 
@@ -1151,12 +1213,9 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
   if (((uintptr_t)d->x | (uintptr_t)d->w | (d->out_mode == ODTK_OUT_CANDIDATES ? 0 : (uintptr_t)d->y)) & 15) return ODTK_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!configure_kernels()) return ODTK_E_CUDA;
-  }
+  const DeviceState *dstate = device_state(stream);
+  if (!dstate) return ODTK_E_CUDA;
+  const int g_num_sms = dstate->num_sms;
   ConvParams p;
   memset(&p, 0, sizeof p);
   p.N = d->n; p.H = d->h; p.W = d->width; p.Cin = d->cin; p.Cout = d->cout;
@@ -1288,7 +1347,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   static int bias_mma_on = -1;
   if (bias_mma_on < 0) { const char *e = getenv("ODTK_CONV_BIAS_MMA"); bias_mma_on = e ? atoi(e) : 1; }
   if (bias_mma_on && d->bias_op && d->bias) {
-    const void *ones = ones_operand(stream);
+    const void *ones = dstate->ones;
     uint64_t dimsO[2] = {64, 128}, strO[1] = {128};
     uint32_t boxO[2] = {64, 128};
     uint64_t dimsB[2] = {64, (uint64_t)d->cout}, strB[1] = {128};
@@ -1301,7 +1360,10 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (cluster_on < 0) { const char *e = getenv("ODTK_CONV_CLUSTER"); cluster_on = e ? atoi(e) : 2; }   // 0 off, 1 multicast, 2 cta_group::2
   static int cluster_1x1 = -1;
   if (cluster_1x1 < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_1X1"); cluster_1x1 = e ? atoi(e) : 0; }   // measured: 1x1 layers are faster unclustered with the TMA-store epilogue (+2.6 % per step)
-  if (cluster_on && BN > 128 && !d->upsample && !d->residual && (cluster_1x1 || d->ksize == 3) &&
+  static int cluster_res = -1;
+  if (cluster_res < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_RES"); cluster_res = e ? atoi(e) : 0; }   // 1x1 + residual layers as multicast pairs (weights read once per pair from L2)
+  const bool res_pair = cluster_res && d->residual && d->ksize == 1 && stride == 1 && BN == 256 && d->cout % 256 == 0;
+  if (cluster_on && BN > 128 && !d->upsample && (!d->residual || res_pair) && (cluster_1x1 || d->ksize == 3 || res_pair) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
@@ -1314,8 +1376,8 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
       ok = encode_map(&tmBias, d->bias_op, 2, dimsB, strB, boxB);
     }
     if (ok) {
-      p.cluster2 = cluster_on >= 2 ? 2 : 1;
-      p.tma_store = 0;
+      p.cluster2 = (cluster_on >= 2 && !res_pair) ? 2 : 1;   // residual pairs: cta_group::1 MMAs, multicast weights
+      if (!(res_pair && cluster_res >= 2)) p.tma_store = 0;
       if (p.cluster2 == 2) { p.nstages = kPipeBytes / (kABytes + BN * 64); if (p.nstages > kMaxStages) p.nstages = kMaxStages; }
     }
     else return ODTK_E_CUDA;
@@ -1326,7 +1388,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (res_mma_on < 0) { const char *e = getenv("ODTK_CONV_RES_MMA"); res_mma_on = e ? atoi(e) : 1; }
   if (res_mma_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN == 256 && d->cout % 256 == 0 &&
       (p.ldr % 8) == 0 && (((uintptr_t)d->residual) & 15) == 0) {
-    const void *ident = ident_operand(stream);
+    const void *ident = dstate->ident;
     uint64_t dimsR[2] = {(uint64_t)p.ldr, (uint64_t)p.M}, strR[1] = {(uint64_t)p.ldr * 2};
     uint32_t boxR[2] = {64, 128};
     uint64_t dimsI[2] = {128, 128}, strI[1] = {256};
@@ -1355,6 +1417,8 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
+  g_last_plan = odtk_conv_plan_t{p.mode, p.cluster2, p.BN, p.num_m_tiles, p.num_n_tiles, p.nstages, p.npatch, p.tile_t,
+                                 p.b_resident, p.bias_mma, p.res_mma, p.tma_store, p.TH, p.TW, grid, p.up_mma};
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
     launch_conv(grid, stream, tmA, tmB, tmC, tmOnes, tmBias, tmRes, tmIdent, p);
@@ -1374,12 +1438,9 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   if ((h & 1) || (width & 1) || cout % 16 || cout > 256) return ODTK_E_UNSUPPORTED;
   if (((uintptr_t)xp | (uintptr_t)w | (uintptr_t)y) & 15) return ODTK_E_INVALID;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!configure_kernels()) return ODTK_E_CUDA;
-  }
+  const DeviceState *dstate = device_state(stream);
+  if (!dstate) return ODTK_E_CUDA;
+  const int g_num_sms = dstate->num_sms;
   const int OH = h / 2, OW = width / 2, HP = h + 6, WP = width + 8;
   if ((long long)n * OH * OW >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
   ConvParams p;
@@ -1407,7 +1468,16 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   p.tiles_w = (OW + p.TW - 1) / p.TW;
   p.num_m_tiles = n * p.tiles_h * p.tiles_w;
   CUtensorMap tmA, tmB;
-  if (raw) {
+  static int stem_rows = -1;
+  if (stem_rows < 0) { const char *e = getenv("ODTK_STEM_ROWS"); stem_rows = e ? atoi(e) : 1; }
+  if (raw && stem_rows) {
+    // padded image [n, HP, WP, 4] as rows of WP*4 elements: patch = 37 rows x 96 elements (192 B) -- 37 TMA rows per tile
+    p.stem_rows = 1;
+    uint64_t dims[3] = {(uint64_t)WP * 4, (uint64_t)HP, (uint64_t)n};
+    uint64_t str[2] = {(uint64_t)WP * 8, (uint64_t)HP * WP * 8};
+    uint32_t box[3] = {kStemPatchW * 4, 37, 1};
+    if (!encode_map(&tmA, xp, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return ODTK_E_UNSUPPORTED;
+  } else if (raw) {
     // padded image [n, HP, WP, 4] viewed as 16-byte pixel pairs: {8 el, WP/2, HP, n}; patch = 12 pairs x 37 rows
     uint64_t dims[4] = {8, (uint64_t)WP / 2, (uint64_t)HP, (uint64_t)n};
     uint64_t str[3] = {16, (uint64_t)WP * 8, (uint64_t)HP * WP * 8};
@@ -1427,6 +1497,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   }
   const int total = p.num_m_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
+  g_last_plan = odtk_conv_plan_t{p.mode, 0, p.BN, p.num_m_tiles, 1, p.nstages, 0, 0, 0, 0, 0, 0, p.TH, p.TW, grid, 0};
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
     launch_conv(grid, stream, tmA, tmB, tmB, tmB, tmB, tmB, tmB, p);
@@ -1439,4 +1510,17 @@ extern "C" int odtk_conv_pack_bias(const float *bias, void *out, int cout, odtk_
   if (!bias || !out || cout <= 0) return ODTK_E_INVALID;
   pack_bias_kernel<<<(cout * 64 + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(bias, (__half *)out, cout);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+// What the last odtk_conv2d / odtk_stem_conv call of THIS host thread launched (tests assert which kernel variant ran).
+extern "C" int odtk_conv_last_plan(odtk_conv_plan_t *out) {
+  if (!out) return ODTK_E_INVALID;
+  *out = g_last_plan;
+  return ODTK_OK;
+}
+extern "C" int odtk_conv_map_cache_stats(long long *hits, long long *misses) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (hits) *hits = g_map_hits;
+  if (misses) *misses = g_map_misses;
+  return ODTK_OK;
 }

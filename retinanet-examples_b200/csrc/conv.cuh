@@ -28,6 +28,8 @@ struct ConvParams {
                         // 1: transposed, 8 rows x 16 columns (m -> (m % 8, m / 8)), patch stored column-major
   int b_resident;       // halo mode: all weight blocks (+ the bias block) fit next to the patches and are loaded once per CTA
   int halo_boff;        // put (start address >> 7) & 7 into the descriptor's base-offset field
+  int up_mma;           // FPN upsample-add on the tensor core: D += U * P (U = constant 128 x 64 nearest-upsample selection matrix)
+  int stem_rows;        // mode 5: the patch is loaded as 37 rows of 192 B (3-D map) instead of 444 pieces of 16 B (4-D map)
   // out_mode ODTK_OUT_CANDIDATES: the decode workspace of this pyramid level (decode.cu)
   int *cand_counts;          // [N]
   unsigned *cand_hist;       // [N, cand_hist_bins]

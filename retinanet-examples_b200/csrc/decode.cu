@@ -28,6 +28,8 @@
 // key (slow, exact).  Compile with -fmad=false (see Makefile).
 #include <stdlib.h>
 
+#include <memory>
+
 #include "common.cuh"
 #include "prof.cuh"
 
@@ -485,8 +487,10 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
   if (num_levels > kMaxLevels || top_n > ODTK_MAX_TOP_N || num_anchors > (size_t)kMaxAnchors)
     return ODTK_E_UNSUPPORTED;
   if (num_anchor_floats != 0 && num_anchor_floats != 4 * num_anchors) return ODTK_E_INVALID;
-  static DecodeParams P;  // large: keep it off the stack (host-side staging only)
-  DecodeParams &p = P;
+  // large (level descriptors + anchor tables): heap-allocated per call, so concurrent callers on different host
+  // threads / streams never share staging state (the kernels take it by value at launch)
+  std::unique_ptr<DecodeParams> staging(new DecodeParams);
+  DecodeParams &p = *staging;
   const int slots = num_levels * batch;
   long long cand_entries = 0, total_n = 0;
   for (int l = 0; l < num_levels; l++) {
@@ -516,7 +520,7 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
   cudaStream_t stream = (cudaStream_t)stream_;
   char *base = (char *)workspace;
 
-  // filter grid: one wave of resident CTAs (55 registers x 256 threads -> 4 per SM) x 148 SMs,
+  // filter grid: one wave of resident CTAs (55 registers x 256 threads -> 4 per SM) x the device's SM count,
   // split between levels by bytes.  ODTK_FILTER_CTAS_PER_SM overrides (tuning knob).
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
@@ -524,7 +528,7 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
     ctas_per_sm = e ? atoi(e) : 12;  // measured on B200: 4 -> 3.7, 6 -> 4.67, 12 -> 4.79 TB/s
     if (ctas_per_sm < 1) ctas_per_sm = 12;
   }
-  const long long budget = 148ll * ctas_per_sm;
+  const long long budget = (long long)odtk_sm_count() * ctas_per_sm;
   int blk = 0;
   for (int l = 0; l < num_levels; l++) {
     LevelDesc &L = p.lv[l];

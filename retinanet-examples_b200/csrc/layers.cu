@@ -152,7 +152,7 @@ __global__ void preprocess_u8_kernel(const unsigned char *__restrict__ x, __half
 
 inline int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
-  long long cap = 148ll * 16;
+  long long cap = (long long)odtk_sm_count() * 16;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 

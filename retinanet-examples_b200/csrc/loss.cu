@@ -149,7 +149,7 @@ __global__ void focal_loss_finish_kernel(const double *partials, int n, float *o
 int loss_grid(long long n) {
   long long b = (n / 4 + kThreads - 1) / kThreads / 4;
   if (b < 1) b = 1;
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > odtk_sm_count() * 8) b = odtk_sm_count() * 8;
   return (int)b;
 }
 

@@ -354,12 +354,15 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
 template <int NBOX>
 long long launch_nms(const NmsParams &p, int batch, cudaStream_t stream) {
   const size_t smem = sizeof(typename NmsSmem<NBOX>::U);
-  static bool configured = false;  // per template instance
-  if (!configured) {
+  // the > 48 KB dynamic shared memory opt-in is a per-device function attribute: once per (template instance, device)
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ODTK_E_CUDA;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     if (cudaFuncSetAttribute(nms_batched_kernel<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
       return ODTK_E_CUDA;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   {
     OdtkProfScope prof(ODTK_PROF_NMS, stream);

@@ -36,6 +36,13 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def last_plan():
+    """The kernel variant the last conv launch of this thread used (odtk_conv_last_plan), as a dict."""
+    pl = _lib.ConvPlan()
+    _lib.check(_lib.lib().odtk_conv_last_plan(ctypes.byref(pl)), "conv_last_plan")
+    return {n: getattr(pl, n) for n, _ in pl._fields_}
+
+
 def fold_bn(weight, bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
     """conv (no bias) followed by eval-mode BatchNorm == conv with scaled weights + a bias
     (torchvision BasicBlock/Bottleneck, odtk/backbones/layers.py:5-15).  fp32 in, fp32 out."""
