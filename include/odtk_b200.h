@@ -150,8 +150,9 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
  * convolution kernel of its own (cuDNN through PyTorch).  Activations are NHWC fp16,
  * weights [Cout, ksize*ksize*Cin] fp16 (tap-major, channel-minor), fp32 accumulation.
  * odtk_conv2d handles 1x1 and 3x3 (pad ksize/2) convolutions with Cin % 64 == 0 on the
- * tensor cores, stride 1 or (even sizes) stride 2; odd-sized strided convolutions are first
- * lowered to GEMM rows with odtk_lower_conv and run as a 1x1 convolution over that matrix. */
+ * tensor cores, stride 1 or stride 2 (even sizes: parity-split view; odd sizes: element-strided TMA
+ * boxes), all im2col-free.  odtk_lower_conv (explicit receptive-field gather) remains for callers
+ * with Cin % 64 != 0. */
 #define ODTK_OUT_NHWC_F16 0          /* y: [N, H, W, ldy] fp16                          */
 #define ODTK_OUT_NCHW_F32 1          /* y: [N, Cout, H, W] fp32 (box head output)       */
 #define ODTK_OUT_NCHW_F32_SIGMOID 2  /* same, sigmoid applied (odtk/model.py:140)       */
@@ -164,7 +165,7 @@ typedef struct {
   const void *upsample; /* NHWC fp16 [n, h/2, width/2, cout] nearest-upsampled and added */
   void *y;
   int n, h, width, cin, cout, ksize, relu, out_mode, ldy, ldr;
-  int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2) on even h, width; y is [n, h/2, width/2, ...] */
+  int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2); y is [n, (h-1)/2+1, (width-1)/2+1, ...] */
   const void *bias_op;  /* optional: bias packed by odtk_conv_pack_bias ([cout, 64] fp16).  When given, the
                            bias is added by ONE extra K block on the tensor core instead of in the epilogue */
   const odtk_cand_sink_t *sink; /* out_mode ODTK_OUT_CANDIDATES: where the candidates go (host struct)       */
@@ -195,6 +196,14 @@ int odtk_lower_conv(const void *x, void *out, int n, int h, int w, int c, int ks
 int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_stream_t stream);
 int odtk_stem_conv(const void *xp, const void *w, const float *bias, void *y, int n, int h, int width,
                    int cout, int relu, odtk_stream_t stream);
+/* Stem + max-pool fused (B200-native): 7x7/2 convolution + bias (folded BatchNorm) + ReLU + 3x3/2 pad-1 max-pool in one
+ * kernel; the [n, h/2, w/2, 64] stem activation is never written.  xp, w as for odtk_stem_conv; cout must be 64;
+ * y: NHWC fp16 [n, (h/2 - 1)/2 + 1, (w/2 - 1)/2 + 1, 64].  Bit-identical to odtk_stem_conv followed by
+ * odtk_maxpool3x3s2 (the same fp16 values are pooled).                                                        */
+int odtk_stem_pool(const void *xp, const void *w, const float *bias, void *y, int n, int h, int width, int cout,
+                   int relu, odtk_stream_t stream);
+/* y = max(x, 0), fp16, n % 8 == 0, 16-byte aligned (input of FPN pyramid7: ReLU(P6), odtk/backbones/fpn.py:55). */
+int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t stream);
 /* 3x3 stride-2 pad-1 max-pool, NHWC fp16 (torchvision resnet stem).                  */
 int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, int c, odtk_stream_t stream);
 

@@ -46,10 +46,11 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "prof.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;   // narrow-N layers stream small weight blocks: depth, not bytes, hides the L2 latency
 constexpr int kPipeBytes = 4 * (128 * 128 + 256 * 128);   // pipeline region: 4 stages at BN = 256, up to 8 at small BN
 #ifndef ODTK_EPI_WARPS
 #define ODTK_EPI_WARPS 8   /* measured on B200: 8 warps (168 regs, no spills) 1137 img/s vs 16 warps (96 regs, spills) 961 */
@@ -59,178 +60,11 @@ constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16
 constexpr int kBBytesMax = 256 * 128;       // up to 256 rows x 64 fp16
 constexpr int kSlabRowBytes = 128;            // 64 fp16, no padding: 16-byte units are XOR-swizzled with (row & 7)
 constexpr int kSlabBytes = 32 * kSlabRowBytes; // per epilogue warp
-constexpr int kSmemBytes = kPipeBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kSlabBytes;
+constexpr int kBarrierBytes = 512;
+constexpr int kSmemBytes = kPipeBytes + 1024 /*align slack*/ + kBarrierBytes + kEpiWarps * kSlabBytes;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
-
-// ---------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                            int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// cta_group::2 TMA loads: destination in the executing CTA, completion counted on a barrier that may live in the peer
-__device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_5d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// One lane of a fully converged warp.  The issuing warps stay converged and wrap only the TMA / MMA / commit
-// instructions in `if (elect_one())`: their operands then live in uniform registers, instead of the per-instruction
-// "waterfall" loops (ELECT + R2UR.BROADCAST + branch) the compiler emits around them in lane-0-only code.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {   // arrive on the same barrier in every CTA of `mask`
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar, uint16_t mask) {   // cta_group::2 commit, arrives in every CTA of `mask`
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 64 fp16 = 128 B, 8-row
-// groups 1024 B apart (SBO), LBO unused for swizzled K-major layouts, descriptor version 1.
-// `row_bytes` = 128 (SWIZZLE_128B, layout type 2) or 64 (SWIZZLE_64B, layout type 4): the 8-row
-// swizzle atom is 8 * row_bytes.
-__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, int row_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address  [0,14)
-  d |= (uint64_t)1 << 16;                              // LBO (ignored)  [16,30)
-  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;         // SBO            [32,46)
-  d |= (uint64_t)1 << 46;                              // version = 1    [46,48)
-  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;     // swizzle mode   [61,64)
-  return d;
-}
-
-// MN-major operand (N contiguous), 128-byte swizzle: 64-element (128 B) chunks along N are `lbo` bytes apart,
-// 8-row groups along K are 1024 B apart.  Used for the residual tile read as the B operand of I * R.
-__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr, uint32_t lbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // Halo mode: view of the patch [18][16 pixels][64 ch] (pixel pitch 128 B, patch-row pitch 2048 B) shifted by a tap.
 // 8-row groups (8 consecutive pixels) are 2048 B apart; the 128-byte swizzle phase of the first row is
@@ -257,14 +91,6 @@ constexpr int kStemPatchW = 24;                         // padded pixels per pat
 constexpr int kStemPatchRowBytes = kStemPatchW * 8;     // 192
 constexpr int kStemPatchBytes = 37 * kStemPatchRowBytes;  // 2*16 + 5 rows
 constexpr int kStemPatchSlot = 8192;
-__device__ __forceinline__ uint64_t make_desc_raw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;                                             // layout type 0: no swizzle
-}
 
 struct Barriers {
   uint64_t full[kMaxStages];
@@ -276,9 +102,7 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-// sigmoid with the SFU approximations (ex2.approx + rcp.approx): relative error < 1e-6, far inside
-// the 1e-3 score tolerance, and ~4x fewer instructions than expf + IEEE division in a hot epilogue
-__device__ __forceinline__ float sigmoidf_accurate(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+static_assert(sizeof(Barriers) <= kBarrierBytes, "barrier block too small");
 
 // ---------------------------------------------------------------------------------- kernel
 template <int CPW, bool UPS, int CL>   // CL: 0 = single CTAs; 1 = 2-CTA cluster, weight tile multicast; 2 = 2-CTA cluster, cta_group::2 MMA (M = 256 per pair, each CTA holds half of the weight tile); CPW: 16-column chunks per epilogue segment (1, 2, 4 for BN <= 64, 128, 256); UPS: FPN upsample-add
@@ -353,12 +177,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {   // whole warp converged; one elected lane arms the barriers and issues the TMA loads
       int stage = 0;
       uint32_t phase = 0, rphase = 0;
-      unsigned char *sres = smem + 2 * (kABytes + kBBytesMax);          // 64 KB residual tile (res_mma: 2 stages only)
-      unsigned char *sident = sres + 4 * kABytes;                        // 32 KB identity
+      // res_mma: 2 stages | 64 KB residual tile | 32 KB identity.  up_mma: 3 stages | 32 KB source-pixel tile | 16 KB U
+      unsigned char *sres = smem + (p.up_mma ? 3 : 2) * (kABytes + kBBytesMax);
+      unsigned char *sident = sres + (p.up_mma ? 2 : 4) * kABytes;
       if (p.res_mma && elect_one()) {
         mbar_arrive_expect_tx(&bars->ident_full, 2u * kABytes);
         tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
         tma_load_2d(sident + kABytes, &tmIdent, &bars->ident_full, 64, 0);
+      }
+      if (p.up_mma && elect_one()) {
+        mbar_arrive_expect_tx(&bars->ident_full, (uint32_t)kABytes);
+        tma_load_2d(sident, &tmIdent, &bars->ident_full, 0, 0);
       }
       if (p.mode == 5) {
         // ---- stem, raw-window mode: the 28 KB of weights stay resident; one 7 KB image patch per tile ----
@@ -482,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
                 if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (a_bytes + b_bytes));
                 const int half = p.BN >> 1;
-                if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, w0 + dx, h0 + dy, img);
+                if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
                 else if (p.mode == 3) {
                   const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
                   tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
@@ -494,7 +323,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
-              if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, w0 + dx, h0 + dy, img);
+              if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
               else if (p.mode == 3) {
                 // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
                 const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
@@ -545,6 +374,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           rphase ^= 1u;
         }
+        if (p.up_mma) {
+          // FPN top-down path: the 64 source pixels (rows of the coarser level) that the 128 output pixels of this tile
+          // nearest-upsample from, as four 128B-swizzled 64-channel slices of 64 rows: the MN-major B operand of
+          // D += U * P (U[i][k] = (k == i >> 1)).  Output pixels 16g .. 16g+15 sit in one image row (W % 16 == 0), their
+          // sources are 8 consecutive pixels of one source row: one 8-row box (= one swizzle atom) per group and slice.
+          mbar_wait(&bars->res_empty, rphase ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->res_full, 2u * kABytes);
+            const int hw = p.H * p.W;
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+              long long m = (long long)m_tile * 128 + 16 * g;
+              if (m >= p.M) m = p.M - 16;                       // rows beyond M are never stored: any valid source will do
+              const int im = (int)(m / hw), rem = (int)(m - (long long)im * hw), h = rem / p.W, w = rem - h * p.W;
+              const int src = (im * p.up_h + (h >> 1)) * p.up_w + (w >> 1);
+#pragma unroll
+              for (int j = 0; j < 4; j++) tma_load_2d(sres + j * 8192 + g * 1024, &tmRes, &bars->res_full, n0 + 64 * j, src);
+            }
+          }
+          rphase ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
@@ -555,8 +405,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0, rphase = 0;
       int it = 0;
-      const uint32_t sres = smem_u32(smem + 2 * (kABytes + kBBytesMax)), sident = sres + 4 * kABytes;
-      if (p.res_mma) mbar_wait(&bars->ident_full, 0);
+      const uint32_t sres = smem_u32(smem + (p.up_mma ? 3 : 2) * (kABytes + kBBytesMax)), sident = sres + (p.up_mma ? 2 : 4) * kABytes;
+      if (p.res_mma || p.up_mma) mbar_wait(&bars->ident_full, 0);
       if (p.mode == 5) {
         const uint32_t sw = smem_u32(smem + kMaxStages * kStemPatchSlot);
         mbar_wait(&bars->ident_full, 0);
@@ -693,6 +543,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 8; j++) {   // K = 128 pixels of the tile, 16 per instruction
               const uint64_t da = make_desc_kmajor(sident + (uint32_t)(j >> 2) * kABytes, 128) + (uint64_t)(2 * (j & 3));
               const uint64_t db = make_desc_mnmajor(sres + (uint32_t)j * 2048u, (uint32_t)kABytes);
+              tc_mma_f16(tmem_d, da, db, idesc_r, 1u);
+            }
+            tc_commit(&bars->res_empty);
+          }
+        }
+        if (p.up_mma) {
+          mbar_wait(&bars->res_full, rphase);
+          tc_fence_after();
+          rphase ^= 1u;
+          const uint32_t idesc_r = idesc | (1u << 16);     // B operand MN-major
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {   // K = 64 source pixels, 16 per instruction
+              const uint64_t da = make_desc_kmajor(sident, 128) + (uint64_t)(2 * j);
+              const uint64_t db = make_desc_mnmajor(sres + (uint32_t)j * 2048u, 8192u);
               tc_mma_f16(tmem_d, da, db, idesc_r, 1u);
             }
             tc_commit(&bars->res_empty);
@@ -1137,7 +1002,7 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
   if (cpw1_max < 0) { const char *e = getenv("ODTK_CONV_CPW1_MAX"); cpw1_max = e ? atoi(e) : 2; }
   if (p.cluster2 == 2)   launch_one<4, false, 2>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (p.cluster2)   launch_one<4, false, 1>(grid & ~1, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
-  else if (p.upsample)   launch_one<4, true, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
+  else if (p.upsample && !p.up_mma) launch_one<4, true, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (nchunks <= cpw1_max) launch_one<1, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else if (nchunks <= 8) launch_one<2, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
   else                   launch_one<4, false, 0>(grid, stream, tmA, tmB, tmC, tmO, tmBi, tmR, tmI, p);
@@ -1146,8 +1011,10 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
 // constant operands: the 128 x 128 identity (A operand of the residual MMAs) and the ones tile (A operand of the bias
 // block: 128 rows x 64 fp16, columns 0 and 1 are 1.0).  __device__ globals: one instance per device.
 __device__ __half g_ident_op[128 * 128];
+__device__ __half g_upsel_op[128 * 64];   // U[i][k] = (k == i >> 1): nearest-upsample selection (A operand of the FPN add)
 __device__ __half g_ones_op[128 * 64];
 __global__ void init_const_operands_kernel() {
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_upsel_op[i] = __float2half_rn((i & 63) == (i >> 7) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) g_ident_op[i] = __float2half_rn((i >> 7) == (i & 127) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_ones_op[i] = __float2half_rn((i & 63) < 2 ? 1.0f : 0.0f);
 }
@@ -1173,7 +1040,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready;
   int num_sms;
-  void *ident, *ones;
+  void *ident, *ones, *upsel;
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_dev_mu;
@@ -1186,7 +1053,8 @@ const DeviceState *device_state(cudaStream_t stream) {
   if (d.ready) return &d;
   if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.num_sms <= 0) return nullptr;
   if (!configure_kernels()) return nullptr;
-  if (cudaGetSymbolAddress(&d.ident, g_ident_op) != cudaSuccess || cudaGetSymbolAddress(&d.ones, g_ones_op) != cudaSuccess) return nullptr;
+  if (cudaGetSymbolAddress(&d.ident, g_ident_op) != cudaSuccess || cudaGetSymbolAddress(&d.ones, g_ones_op) != cudaSuccess ||
+      cudaGetSymbolAddress(&d.upsel, g_upsel_op) != cudaSuccess) return nullptr;
   init_const_operands_kernel<<<1, 256, 0, stream>>>();
   if (cudaGetLastError() != cudaSuccess) return nullptr;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1230,6 +1098,20 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     int nt = (d->cout + 255) / 256;
     BN = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
   }
+  {
+    // few tiles (coarse pyramid levels): narrower N tiles put more SMs to work; each CTA's K loop is as long, its MMAs
+    // proportionally shorter.  Only for NHWC outputs whose Cout splits evenly.
+    static int shrink_on = -1;
+    if (shrink_on < 0) { const char *e = getenv("ODTK_CONV_BN_SHRINK"); shrink_on = e ? atoi(e) : 1; }
+    const int st = d->stride > 1 ? 2 : 1;
+    const long long opix = (long long)d->n * ((d->h - 1) / st + 1) * ((d->width - 1) / st + 1);
+    long long mt = (opix + 127) / 128;
+    if (d->ksize == 3 && st == 1) mt = (long long)d->n * ((d->h + 15) / 16) * ((d->width + 7) / 8);   // halo tiles (upper bound)
+    const int sms = odtk_sm_count();
+    while (shrink_on && d->out_mode == ODTK_OUT_NHWC_F16 && !d->upsample && !d->residual && BN > 64 && (BN % 32) == 0 &&
+           d->cout % (BN / 2) == 0 && mt * ((d->cout + BN - 1) / BN) * 2 <= sms)
+      BN /= 2;
+  }
   p.BN = BN;
   p.nstages = kPipeBytes / (kABytes + BN * 128);
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
@@ -1267,7 +1149,29 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   }
   const int stride = d->stride > 1 ? d->stride : 1;
   if (stride != 1 && stride != 2) return ODTK_E_UNSUPPORTED;
-  if (stride == 2) {
+  static int s2_strided_box = -1;
+  if (s2_strided_box < 0) { const char *e = getenv("ODTK_CONV_S2_BOX"); s2_strided_box = e ? atoi(e) : 1; }   // 2: also for even sizes
+  if (stride == 2 && !d->upsample && (((d->h & 1) || (d->width & 1)) ? s2_strided_box >= 1 : s2_strided_box >= 2)) {
+    // stride-2 1x1 / 3x3 (pad ksize/2) on ANY size, im2col-free: one box per tap whose W and H dimensions are
+    // traversed with element stride 2 (boxDim = 2 * pixels, elementStrides = 2: the TMA unit loads every second
+    // pixel); the box origin 2*o + d may be -1 or reach past the edge: zero-filled == padding.
+    const int OH = (d->h - 1) / 2 + 1, OW = (d->width - 1) / 2 + 1;
+    p.mode = 1;
+    p.s2 = 1;
+    p.H = OH; p.W = OW;
+    p.M = (long long)d->n * OH * OW;
+    p.up_h = OH / 2; p.up_w = OW / 2;
+    choose_patch(OH, OW, p.TH, p.TW);
+    p.tiles_h = (OH + p.TH - 1) / p.TH;
+    p.tiles_w = (OW + p.TW - 1) / p.TW;
+    p.num_m_tiles = d->n * p.tiles_h * p.tiles_w;
+    const uint64_t C = (uint64_t)d->cin, W = (uint64_t)d->width, H = (uint64_t)d->h;
+    uint64_t dims[4] = {C, W, H, (uint64_t)d->n};
+    uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+    uint32_t box[4] = {64, (uint32_t)(2 * p.TW), (uint32_t)(2 * p.TH), 1};
+    uint32_t es[4] = {1, 2, 2, 1};
+    if (!encode_map(&tmA, d->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, es)) return ODTK_E_CUDA;
+  } else if (stride == 2) {
     // stride-2 1x1 / 3x3 (pad ksize/2) on even-sized inputs: 5-D parity-split view of the NHWC tensor
     // {2C (column parity x channel), W/2, 2 (row parity), H/2, N}; out-of-range half-rows/columns
     // (the -1 of the top/left taps) are zero-filled by the TMA unit == padding.
@@ -1363,7 +1267,10 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   static int cluster_res = -1;
   if (cluster_res < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_RES"); cluster_res = e ? atoi(e) : 0; }   // 1x1 + residual layers as multicast pairs (weights read once per pair from L2)
   const bool res_pair = cluster_res && d->residual && d->ksize == 1 && stride == 1 && BN == 256 && d->cout % 256 == 0;
-  if (cluster_on && BN > 128 && !d->upsample && (!d->residual || res_pair) && (cluster_1x1 || d->ksize == 3 || res_pair) &&
+  static int two_narrow = -1;
+  if (two_narrow < 0) { const char *e = getenv("ODTK_CONV_TWO_NARROW"); two_narrow = e ? atoi(e) : 0; }   // cta_group::2 pairs for narrow fp32-output head layers (halved weight stream per CTA)
+  const bool narrow_pair = two_narrow && cluster_on >= 2 && p.mode == 4 && p.out_mode != ODTK_OUT_NHWC_F16 && BN >= 32 && BN <= 128;
+  if (cluster_on && (BN > 128 || narrow_pair) && !d->upsample && (!d->residual || res_pair) && (cluster_1x1 || d->ksize == 3 || res_pair) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
@@ -1398,6 +1305,21 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
       p.nstages = 2;   // the rest of the pipeline region holds the residual tile (64 KB) and the identity (32 KB)
     }
   }
+  // FPN upsample-add on the tensor core (D += U * P): 1x1 lateral layers whose rows split into 16-pixel groups
+  static int up_mma_on = -1;
+  if (up_mma_on < 0) { const char *e = getenv("ODTK_CONV_UP_MMA"); up_mma_on = e ? atoi(e) : 1; }
+  if (up_mma_on && d->upsample && !d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN == 256 &&
+      d->cout % 256 == 0 && d->width % 16 == 0 && !p.cluster2 && (((uintptr_t)d->upsample) & 15) == 0) {
+    const uint64_t msrc = (uint64_t)d->n * p.up_h * p.up_w;
+    uint64_t dimsR[2] = {(uint64_t)d->cout, msrc}, strR[1] = {(uint64_t)d->cout * 2};
+    uint32_t boxR[2] = {64, 8};
+    uint64_t dimsU[2] = {64, 128}, strU[1] = {128};
+    uint32_t boxU[2] = {64, 128};
+    if (encode_map(&tmRes, d->upsample, 2, dimsR, strR, boxR) && encode_map(&tmIdent, dstate->upsel, 2, dimsU, strU, boxU)) {
+      p.up_mma = 1;
+      p.nstages = 3;   // the fourth stage's 48 KB hold the source-pixel tile (32 KB) and U (16 KB)
+    }
+  }
   if (p.mode == 4) {   // pipeline region: patches | ones tile (bias block) | weight-block stages
     const int bstage = (p.cluster2 == 2 ? BN / 2 : BN) * 128;
     const int fixed = p.bias_mma ? kABytes : 0;
@@ -1415,6 +1337,9 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     if (p.nstages > kMaxStages) p.nstages = kMaxStages;
     if (p.nstages < 2) return ODTK_E_UNSUPPORTED;
   }
+  static int max_stages = -1;
+  if (max_stages < 0) { const char *e = getenv("ODTK_CONV_MAX_STAGES"); max_stages = e ? atoi(e) : kMaxStages; if (max_stages < 2 || max_stages > kMaxStages) max_stages = kMaxStages; }
+  if (p.nstages > max_stages) p.nstages = max_stages;
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   g_last_plan = odtk_conv_plan_t{p.mode, p.cluster2, p.BN, p.num_m_tiles, p.num_n_tiles, p.nstages, p.npatch, p.tile_t,

@@ -123,6 +123,33 @@ __global__ void pad_input_kernel(const __half *__restrict__ x, __half *__restric
   }
 }
 
+// Same, for W % 8 == 0 (input rows start 16-byte aligned): one block per padded row; the 6-byte pixels of the input row
+// are staged through shared memory with coalesced 16-byte loads, the padded row leaves as coalesced 16-byte stores
+// (two 8-byte pixels each) -- the per-pixel version above issues three 2-byte loads per pixel.
+__global__ void pad_input_rows_kernel(const __half *__restrict__ x, __half *__restrict__ y, int N, int H, int W) {
+  extern __shared__ uint4 srow[];                                 // W * 6 bytes of the input row
+  const int HP = H + 6, WP = W + 8;
+  const int n = blockIdx.x / HP, yp = blockIdx.x - n * HP, ih = yp - 3;
+  uint4 *dst = reinterpret_cast<uint4 *>(y + ((long long)n * HP + yp) * WP * 4);
+  const int pairs = WP / 2;
+  if (ih < 0 || ih >= H) {
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const uint4 *src = reinterpret_cast<const uint4 *>(x + ((long long)n * H + ih) * W * 3);
+  const int nv = W * 6 / 16;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) srow[i] = __ldg(src + i);
+  __syncthreads();
+  const unsigned short *s = reinterpret_cast<const unsigned short *>(srow);
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int iw0 = 2 * i - 3, iw1 = iw0 + 1;
+    if (iw0 >= 0 && iw0 < W) { v.x = (unsigned)s[iw0 * 3] | ((unsigned)s[iw0 * 3 + 1] << 16); v.y = (unsigned)s[iw0 * 3 + 2]; }
+    if (iw1 >= 0 && iw1 < W) { v.z = (unsigned)s[iw1 * 3] | ((unsigned)s[iw1 * 3 + 1] << 16); v.w = (unsigned)s[iw1 * 3 + 2]; }
+    dst[i] = v;
+  }
+}
+
 // Input side of odtk infer (reference odtk/data.py:113-123): uint8 HWC image -> /255 -> (x - mean) / std
 // -> zero padding to a multiple of the model stride, fused with the stem's own zero padding and the
 // RGB -> NHWC4 widening: one 8-byte store per padded pixel, the fp32 full-image pass disappears.
@@ -147,6 +174,18 @@ __global__ void preprocess_u8_kernel(const unsigned char *__restrict__ x, __half
       v.y = *reinterpret_cast<unsigned *>(&bz);
     }
     reinterpret_cast<uint2 *>(y)[i] = v;
+  }
+}
+
+// y = max(x, 0) on fp16, 8 elements per thread (FPN pyramid7 reads ReLU(P6), fpn.py:55, while P6 itself is an output)
+__global__ void relu_f16_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, long long n8) {
+  const __half2 z = __float2half2_rn(0.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v = __ldg(x + i);
+    __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __hmax2(h[j], z);
+    y[i] = v;
   }
 }
 
@@ -193,7 +232,10 @@ extern "C" int odtk_pad_input(const void *x, void *y, int n, int h, int w, odtk_
   if (!x || !y || n <= 0 || h <= 0 || w <= 0) return ODTK_E_INVALID;
   long long total = (long long)n * (h + 6) * (w + 8);
   OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
-  pad_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
+  if (w % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (size_t)w * 6 <= 48 * 1024 && (long long)n * (h + 6) < (1ll << 31))
+    pad_input_rows_kernel<<<n * (h + 6), 256, (size_t)w * 6, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
+  else
+    pad_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, h, w);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
 
@@ -204,5 +246,12 @@ extern "C" int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, i
   OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
   preprocess_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
       (const unsigned char *)x, (__half *)y, n, h, w, hs, ws, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t stream_) {
+  if (!x || !y || n <= 0 || (n % 8) || (((uintptr_t)x | (uintptr_t)y) & 15)) return ODTK_E_INVALID;
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
+  relu_f16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4 *)x, (uint4 *)y, n / 8);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -74,7 +74,7 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
     assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
     n, h, wd, cin = x.shape
-    oh, ow = (h // 2, wd // 2) if stride == 2 else (h, wd)
+    oh, ow = ((h - 1) // 2 + 1, (wd - 1) // 2 + 1) if stride == 2 else (h, wd)
     if out_mode == OUT_CANDIDATES:
         assert sink is not None
     elif out is None:
@@ -114,6 +114,16 @@ def lower_conv(x, ksize, stride, pad, kpad=None, relu=False):
                                           ksize, stride, pad, kpad, int(relu), _stream()), "lower_conv")
     STATS["launches"] += 1
     _trace("lower_conv", 0, x.numel() * 2 + out.numel() * 2, n=n, h=h, w=w, cin=c)
+    return out
+
+
+def relu(x):
+    """max(x, 0) into a new tensor (input of FPN pyramid7, odtk/backbones/fpn.py:55)."""
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().odtk_relu_f16(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), x.numel(), _stream()),
+               "relu_f16")
+    STATS["launches"] += 1
+    _trace("relu", 0, x.numel() * 4, n=x.shape[0], h=x.shape[1], w=x.shape[2], cin=x.shape[3])
     return out
 
 
@@ -186,3 +196,29 @@ def stem_conv(x, w, bias, cout, relu=True):
     _trace("stem7x7", 2 * out.numel() * 147, xp.numel() * 2 + w.numel() * 2 + out.numel() * 2, n=n, h=h, w=wd, cin=3,
            cout=cout, stride=2)
     return out
+
+
+def stem_pool_padded(xp, h, wd, w, bias, cout, relu=True):
+    """Stem conv + BN + ReLU + 3x3/2 max-pool in ONE kernel over a padded NHWC4 buffer [N, h+6, wd+8, 4] (odtk_stem_pool):
+    the stem activation is never written.  Returns NHWC fp16 [N, (h/2-1)/2+1, (wd/2-1)/2+1, cout]."""
+    n = xp.shape[0]
+    oh, ow = h // 2, wd // 2
+    out = torch.empty((n, (oh - 1) // 2 + 1, (ow - 1) // 2 + 1, cout), dtype=torch.float16, device=xp.device)
+    _lib.check(_lib.lib().odtk_stem_pool(ctypes.c_void_p(xp.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+                                         ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                         ctypes.c_void_p(out.data_ptr()), n, h, wd, cout, int(relu), _stream()), "stem_pool")
+    STATS["launches"] += 1
+    _trace("stem_pool", 2 * n * oh * ow * cout * 147, xp.numel() * 2 + w.numel() * 2 + out.numel() * 2, n=n, h=h, w=wd, cin=3,
+           cout=cout, stride=2)
+    return out
+
+
+def stem_pool(x, w, bias, cout, relu=True):
+    """NHWC fp16 RGB batch [N,H,W,3] -> zero-pad to NHWC4 (one small kernel) -> fused stem + max-pool."""
+    n, h, wd, c = x.shape
+    assert c == 3 and x.dtype == torch.float16 and x.is_contiguous()
+    xp = torch.empty((n, h + 6, wd + 8, 4), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().odtk_pad_input(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, wd, _stream()), "pad_input")
+    STATS["launches"] += 1
+    _trace("pad_input", 0, x.numel() * 2 + xp.numel() * 2, n=n, h=h, w=wd, cin=3)
+    return stem_pool_padded(xp, h, wd, w, bias, cout, relu)

@@ -114,9 +114,11 @@ class _Conv:
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode,
                                  bias_op=self.bop, sink=sink)
         assert sink is None
-        if (self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and not in_relu and upsample is None
-                and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0):
-            # even-sized stride-2 convolution: strided TMA view, no gather pre-pass
+        if self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and upsample is None:
+            # stride-2 convolution, any size: strided TMA view (even sizes: parity split, odd sizes: element-strided
+            # boxes), no gather pre-pass; ReLU on the input (FPN pyramid7) is one tiny elementwise launch
+            if in_relu:
+                x = engine.relu(x)
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2,
                                  bias_op=self.bop)
         low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
@@ -155,6 +157,7 @@ class Model:
         self.device = None
         self.parallel_heads = True
         self.fused_candidates = os.environ.get("ODTK_FUSED_CANDIDATES", "1") != "0"
+        self.fused_stem = os.environ.get("ODTK_FUSED_STEM", "1") != "0"
         self._fused = {}
         self._head_streams = None
 
@@ -238,11 +241,29 @@ class Model:
         self._packed = P
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _features(self, x, stem_done=False):
+    def _stem(self, x=None, padded=None):
+        """conv1 + bn1 + relu + maxpool (odtk/backbones/resnet.py:25-28).  One fused kernel when the stem has the
+        standard 64 output channels and the image size is even; `padded` = (xp, h, w) from engine.preprocess_u8."""
+        stem = self._packed["stem"]
+        if padded is not None:
+            xp, h, w = padded
+            n = xp.shape[0]
+        else:
+            n, h, w = x.shape[0], x.shape[1], x.shape[2]
+        engine.STATS["conv_flops"] += 2 * n * (h // 2) * (w // 2) * stem.cout * 49 * 3
+        fused = self.fused_stem and stem.stem and stem.cout == 64 and h % 2 == 0 and w % 2 == 0
+        if padded is not None:
+            if fused:
+                return engine.stem_pool_padded(xp, h, w, stem.w_stem, stem.b, stem.cout, relu=True)
+            return engine.maxpool3x3s2(engine.stem_conv_padded(xp, h, w, stem.w_stem, stem.b, stem.cout, relu=True))
+        if fused:
+            return engine.stem_pool(x, stem.w_stem, stem.b, stem.cout, relu=True)
+        engine.STATS["conv_flops"] -= 2 * n * (h // 2) * (w // 2) * stem.cout * 49 * 3      # _Conv.__call__ counts it
+        return engine.maxpool3x3s2(stem(x, relu=True))
+
+    def _features(self, x):
+        """`x`: the POOLED stem output [N, H/4, W/4, 64] (from _stem)."""
         P = self._packed
-        if not stem_done:
-            x = P["stem"](x, relu=True)
-        x = engine.maxpool3x3s2(x)
         outs = {}
         for blk in P["blocks"]:
             identity = x if blk["down"] is None else blk["down"](x)
@@ -322,17 +343,14 @@ class Model:
             raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
         P = self._packed
         xp, hs, ws = engine.preprocess_u8(images, self.stride)
-        stem = P["stem"]
-        engine.STATS["conv_flops"] += 2 * images.shape[0] * (hs // 2) * (ws // 2) * stem.cout * 49 * 3
-        x = engine.stem_conv_padded(xp, hs, ws, stem.w_stem, stem.b, stem.cout, relu=True)
-        return self._heads(self._features(x, stem_done=True), sigmoid), (hs, ws)
+        return self._heads(self._features(self._stem(padded=(xp, hs, ws))), sigmoid), (hs, ws)
 
     def forward_heads(self, x, sigmoid=True):
         """The `exporting=True` view of the reference (odtk/model.py:142-144): per-level
         (sigmoid) class maps [B, A*C, H, W] and box maps [B, A*4|6, H, W], fp32 NCHW."""
         if self._packed is None:
             raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
-        return self._heads(self._features(self._to_nhwc_half(x)), sigmoid)
+        return self._heads(self._features(self._stem(self._to_nhwc_half(x))), sigmoid)
 
     def _level_anchors(self, widths, width):
         strides, anchors = [], []
@@ -354,13 +372,10 @@ class Model:
             raise RuntimeError("call .cuda() after loading weights: there is no CPU path")
         if x.dtype == torch.uint8:
             xp, hs, width = engine.preprocess_u8(x, self.stride)
-            stem = self._packed["stem"]
-            engine.STATS["conv_flops"] += 2 * x.shape[0] * (hs // 2) * (width // 2) * stem.cout * 49 * 3
-            features = self._features(engine.stem_conv_padded(xp, hs, width, stem.w_stem, stem.b, stem.cout, relu=True),
-                                      stem_done=True)
+            features = self._features(self._stem(padded=(xp, hs, width)))
         else:
             width = x.shape[-1]
-            features = self._features(self._to_nhwc_half(x))
+            features = self._features(self._stem(self._to_nhwc_half(x)))
         sizes = tuple((f.shape[1], f.shape[2]) for f in features)
         batch = features[0].shape[0]
         key = (batch, sizes, width, self.threshold, self.top_n, self.rotated_bbox)

@@ -202,3 +202,120 @@ def test_stem_raw_window_mode_edges(n, h, w):
     x, wt, b = _rand((n, h, w, 3), g), _rand((64, 3, 7, 7), g, 0.1), torch.randn(64, generator=g)
     y = engine.stem_conv(x.to(DEV), engine.pack_stem_weight(wt.float()).to(DEV), b.to(DEV), 64, relu=True)
     _close16(y, _ref_conv(x, wt, b, 7, relu=True, stride=2, pad=3))
+
+
+# ---- round 2: kernel-variant assertions (odtk_conv_last_plan), tensor-core upsample-add, element-strided stride 2 -----
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 26, 48, 256, 256), (1, 100, 160, 512, 256), (3, 10, 16, 1024, 256),
+                                           (1, 50, 80, 128, 512)])
+def test_upsample_add_on_the_tensor_core(n, h, w, cin, cout):
+    """FPN lateral 1x1 + nearest-upsample add as D += U * P (W % 16 == 0): exact, like the epilogue add."""
+    g = torch.Generator().manual_seed(h * 17 + w + cin)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 1, 1), g, 0.05), torch.randn(cout, generator=g)
+    up = _rand((n, h // 2, w // 2, cout), g)
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, 1, upsample=up.to(DEV),
+                      bias_op=engine.pack_bias(bd))
+    plan = engine.last_plan()
+    assert plan["up_mma"] == 1 and plan["mode"] == 0 and plan["bn"] == 256, plan
+    _close16(y, _ref_conv(x, wt, b, 1, upsample=up))
+
+
+def test_upsample_add_epilogue_fallback_when_rows_do_not_split():
+    g = torch.Generator().manual_seed(77)
+    n, h, w, cin, cout = 1, 26, 40, 256, 256           # W % 16 != 0
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, 1, 1), g, 0.05), torch.randn(cout, generator=g)
+    up = _rand((n, h // 2, w // 2, cout), g)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), b.to(DEV), cout, 1, upsample=up.to(DEV))
+    assert engine.last_plan()["up_mma"] == 0
+    _close16(y, _ref_conv(x, wt, b, 1, upsample=up))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ks", [(2, 25, 40, 2048, 256, 3), (2, 13, 20, 256, 256, 3), (1, 25, 39, 128, 128, 3),
+                                              (3, 7, 9, 512, 256, 1), (1, 51, 81, 64, 64, 3), (32, 25, 40, 512, 256, 3)])
+def test_strided_conv_odd_sizes_element_strided_tma(n, h, w, cin, cout, ks):
+    """stride-2 convolutions on ODD sizes (FPN pyramid6 / pyramid7 at 25x40 / 13x20): element-strided TMA boxes,
+    no receptive-field gather."""
+    g = torch.Generator().manual_seed(h * 7 + w + cin + ks)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.02), torch.randn(cout, generator=g)
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=True, stride=2,
+                      bias_op=engine.pack_bias(bd))
+    plan = engine.last_plan()
+    assert plan["mode"] == 1, plan
+    assert tuple(y.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cout)
+    _close16(y, _ref_conv(x, wt, b, ks, relu=True, stride=2, pad=ks // 2))
+
+
+def test_relu_copy():
+    g = torch.Generator().manual_seed(3)
+    x = _rand((2, 13, 20, 256), g)
+    y = engine.relu(x.to(DEV))
+    np.testing.assert_array_equal(y.float().cpu().numpy(), F.relu(x.float()).numpy())
+
+
+@pytest.mark.parametrize("shape,ks,kw,expect", [
+    ((4, 100, 160, 256, 256), 3, {}, {"mode": 4, "cluster": 2, "bn": 256}),               # halo, cta_group::2 pairs
+    ((2, 200, 320, 64, 64), 3, {}, {"mode": 4, "b_resident": 1, "bn": 64}),               # resident weights
+    ((2, 50, 80, 256, 1024), 1, {"residual": True}, {"mode": 0, "res_mma": 1, "bn": 256}),  # residual on the tensor core
+    ((2, 200, 320, 256, 64), 1, {}, {"mode": 0, "bn": 64}),
+    ((2, 100, 160, 512, 1024), 1, {"stride": 2}, {"mode": 3}),                             # even stride 2: parity split
+    ((32, 7, 10, 256, 256), 3, {}, {"mode": 4, "bn": 128}),                                # few tiles: narrower N tile
+])
+def test_conv_variant_selection(shape, ks, kw, expect):
+    """The host code picks the kernel variant from the shape; assert which one ran AND that it is right."""
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + ks)
+    x, wt, b = _rand((n, h, w, cin), g), _rand((cout, cin, ks, ks), g, 0.03), torch.randn(cout, generator=g)
+    stride = kw.get("stride", 1)
+    res = _rand((n, h, w, cout), g) if kw.get("residual") else None
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=True,
+                      residual=res.to(DEV) if res is not None else None, stride=stride, bias_op=engine.pack_bias(bd))
+    plan = engine.last_plan()
+    for k, v in expect.items():
+        assert plan[k] == v, (k, plan)
+    _close16(y, _ref_conv(x, wt, b, ks, relu=True, residual=res, stride=stride, pad=ks // 2))
+
+
+def test_tensor_map_cache_hits_on_repeated_calls():
+    import ctypes
+    from retinanet_examples_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    x, wt = _rand((1, 16, 16, 64), g).to(DEV), engine.pack_weight(_rand((64, 64, 3, 3), g, 0.05).float()).to(DEV)
+    out = torch.empty((1, 16, 16, 64), dtype=torch.float16, device=DEV)
+    h0, m0, h1, m1 = (ctypes.c_longlong(0) for _ in range(4))
+    engine.conv2d(x, wt, None, 64, 3, out=out)
+    _lib.lib().odtk_conv_map_cache_stats(ctypes.byref(h0), ctypes.byref(m0))
+    engine.conv2d(x, wt, None, 64, 3, out=out)
+    _lib.lib().odtk_conv_map_cache_stats(ctypes.byref(h1), ctypes.byref(m1))
+    assert m1.value == m0.value and h1.value > h0.value
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 32, 16), (2, 34, 50), (1, 226, 130), (2, 128, 256), (1, 800, 1280), (3, 28, 28)])
+def test_stem_pool_fused_equals_stem_then_maxpool(n, h, w):
+    """conv1 + bn1 + relu + maxpool in one kernel (stem.cu): bit-identical to the two-kernel route (the same fp16
+    values are pooled), and within the fp16 bar of torch's fp32 conv + max_pool2d."""
+    g = torch.Generator().manual_seed(h * 5 + w)
+    x, wt, b = _rand((n, h, w, 3), g), _rand((64, 3, 7, 7), g, 0.1), torch.randn(64, generator=g)
+    ws, bd = engine.pack_stem_weight(wt.float()).to(DEV), b.to(DEV)
+    fused = engine.stem_pool(x.to(DEV), ws, bd, 64, relu=True)
+    two = engine.maxpool3x3s2(engine.stem_conv(x.to(DEV), ws, bd, 64, relu=True))
+    assert fused.shape == two.shape
+    np.testing.assert_array_equal(fused.float().cpu().numpy(), two.float().cpu().numpy())
+    ref = F.max_pool2d(_ref_conv(x, wt, b, 7, relu=True, stride=2, pad=3), 3, 2, 1)
+    _close16(fused, ref)
+
+
+def test_pad_input_rows_kernel_matches_per_pixel_layout():
+    """odtk_pad_input, W % 8 == 0 (row-staged kernel) and W % 8 != 0 (per-pixel kernel): NHWC3 -> zero-bordered NHWC4."""
+    import ctypes
+    from retinanet_examples_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    for (n, h, w) in ((2, 10, 16), (1, 7, 13), (1, 64, 1280)):
+        x = _rand((n, h, w, 3), g).to(DEV)
+        xp = torch.full((n, h + 6, w + 8, 4), 7.0, dtype=torch.float16, device=DEV)
+        _lib.check(_lib.lib().odtk_pad_input(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, w,
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pad_input")
+        ref = torch.zeros((n, h + 6, w + 8, 4), dtype=torch.float16, device=DEV)
+        ref[:, 3:3 + h, 3:3 + w, :3] = x
+        np.testing.assert_array_equal(xp.float().cpu().numpy(), ref.float().cpu().numpy())
