@@ -143,6 +143,17 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
                       int32_t *out_index, void *workspace, size_t workspace_size,
                       odtk_stream_t stream);
 
+/* ---- iou (rotated target assignment) ---------------------------
+ * Replaces odtk::cuda::iou (csrc/cuda/nms_iou.h:33-35, nms_iou.cu:324-387), the kernel behind
+ * odtk._C.iou (csrc/extensions.cpp:47-67,200).
+ *   inputs  = { boxes [num_boxes, 4 corners, (x, y)], anchors [num_anchors, 4, 2] }  fp32
+ *   outputs = { iou [num_anchors, num_boxes] }                                        fp32
+ * Element [a, j]: anchor a (jittered by 0.001 where a coordinate equals the same corner of box j)
+ * clipped against the edges of box j, intersection / (area_a + area_j - intersection), with the
+ * reference's NaN rules.  Same signature as the reference entry point; returns 0 or ODTK_E_*.   */
+int odtk_iou(const void *const *inputs, void *const *outputs, int num_boxes, int num_anchors,
+             odtk_stream_t stream);
+
 /* ---- convolution engine ----------------------------------------------------------
  * Replaces the nn.Conv2d (+ BatchNorm + ReLU + residual / FPN upsample-add) library
  * calls of the reference's Model.forward (odtk/model.py:57-68,130-135;
@@ -173,7 +184,8 @@ typedef struct {
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
 /* Introspection (tests): the kernel variant the last odtk_conv2d / odtk_stem_conv call of the calling host thread
  * launched.  mode: 0 GEMM rows (1x1), 1 shifted box per tap, 3 stride 2, 4 halo (3x3 s1), 5 raw-window stem;
- * cluster: 0 single CTAs, 1 2-CTA multicast pairs, 2 cta_group::2 pairs.                                    */
+ * cluster: 0 single CTAs, 1 2-CTA multicast pairs, 2 cta_group::2 pairs.  res_mma: 1 residual tile as one I * R
+ * product, 2 residual chunks through the pipeline stages (R_j * I64), 0 residual (if any) added in the epilogue.  */
 typedef struct {
   int mode, cluster, bn, num_m_tiles, num_n_tiles, nstages, npatch, tile_t, b_resident, bias_mma, res_mma, tma_store;
   int th, tw, grid, up_mma;
@@ -226,6 +238,24 @@ long long odtk_focal_loss(const float *logits, const float *target, const float 
 long long odtk_smooth_l1_loss(const float *pred, const float *target, const float *mask, long long n,
                               float beta, float grad_scale, float *loss_elem, float *loss_sum, float *grad,
                               void *workspace, size_t workspace_size, odtk_stream_t stream);
+
+/* Model._compute_loss in ONE launch (odtk/model.py:186-210): over all pyramid levels, focal
+ * loss of the class logits against class-index targets with the (depth >= 0) mask, smooth L1 of the box deltas with the
+ * (depth > 0) mask, per-level foreground counts clamp(min=1) summed, both losses divided by that sum -- and, when the
+ * grad pointers are given, the gradients of the two NORMALISED losses w.r.t. the head outputs.  Deterministic (integer
+ * counts, fixed-order double sums).  out: device float[4] = {cls_loss, box_loss, fg_total, 0}.  Two-phase workspace.  */
+typedef struct {
+  const void *cls_logits;   /* [B, A*C, H, W] fp32 raw logits (the heads with exporting / training semantics: no sigmoid) */
+  const void *box_pred;     /* [B, A*nbox, H, W] fp32                                                                    */
+  const int *cls_index;     /* [B, A, H, W] int32: class, -1 background, -2 ignored (odtk_snap_to_anchors)               */
+  const float *box_target;  /* [B, A, nbox, H, W] fp32                                                                   */
+  float *cls_grad;          /* like cls_logits, or NULL                                                                  */
+  float *box_grad;          /* like box_pred, or NULL                                                                    */
+  int height, width;
+} odtk_loss_level_t;
+long long odtk_retina_loss(int batch, int num_levels, const odtk_loss_level_t *levels, int num_anchors, int num_classes,
+                           int nbox, float alpha, float gamma, float beta, float *out, void *workspace,
+                           size_t workspace_size, odtk_stream_t stream);
 
 /* ---- anchor target assignment --------------------------------------------
  * Replaces snap_to_anchors (odtk/box.py:134-186) + box2delta (:67-78) as called per image and level by

@@ -245,6 +245,42 @@ float oracle_rotated_overlap(const float *ib, const float *mb, int fixed_angle) 
   return overlap;
 }
 
+/* iou_cuda_kernel + its host entry point (nms_iou.cu:324-387).  The host function passes
+ * (num_anchors, num_boxes, anchors, boxes) into kernel parameters named (numBoxes, numAnchors,
+ * b_box_vals, a_box_vals) -- nms_iou.cu:385 -- so, in terms of the REAL boxes and anchors:
+ * out[a * nb + j]: rect1 = anchor a (the polygon that is clipped, jittered where equal to the
+ * same corner of box j, :341-349), rect2 = box j (the clip rectangle, :359).                   */
+void oracle_iou(const float *boxes, const float *anchors, int nb, int na, float *out) {
+  for (int a = 0; a < na; a++) {
+    for (int j = 0; j < nb; j++) {
+      f2 inter[KPTS], rect1[4], rect1_s[4], rect2[4], rect2_s[4];
+      for (int k = 0; k < KPTS; k++) { inter[k].x = -1.0f; inter[k].y = -1.0f; }
+      for (int b = 0; b < 4; b++) {
+        f2 pa = {anchors[(a * 4 + b) * 2], anchors[(a * 4 + b) * 2 + 1]};
+        f2 pb = {boxes[(j * 4 + b) * 2], boxes[(j * 4 + b) * 2 + 1]};
+        float px = (pa.x == pb.x) ? 0.001f : 0.0f;
+        float py = (pa.y == pb.y) ? 0.001f : 0.0f;
+        inter[b].x = pa.x + px; inter[b].y = pa.y + py;
+        rect1[b] = pa;
+        rect2[b] = pb;
+      }
+      for (int b = 0; b < 4; b++) { rect1_s[b] = rect1[(b + 1) & 3]; rect2_s[b] = rect2[(b + 1) & 3]; }
+      float ia = intersection_area(rect2, rect2_s, inter);
+      float a1 = 0.0f, a2 = 0.0f;
+      for (int k = 0; k < 4; k++) {
+        a1 += rect1[k].x * rect1_s[k].y - rect1[k].y * rect1_s[k].x;
+        a2 += rect2[k].x * rect2_s[k].y - rect2[k].y * rect2_s[k].x;
+      }
+      float ua = (fabsf(a1) + fabsf(a2)) / 2.0f;
+      float v;
+      if (isnan(ia) && isnan(ua)) v = 1.0f;
+      else if (isnan(ia)) v = 0.0f;
+      else v = ia / (ua - ia);
+      out[(int64_t)a * nb + j] = v;
+    }
+  }
+}
+
 /* nms.cu:57-69 */
 float oracle_aligned_overlap(const float *ib, const float *mb) {
   float x1 = fmaxf(ib[0], mb[0]);

@@ -37,6 +37,8 @@ def lib():
                                  ctypes.c_int, ctypes.c_int, f32p, f32p, f32p, i32p]
         L.oracle_rotated_overlap.restype = ctypes.c_float
         L.oracle_rotated_overlap.argtypes = [f32p, f32p, ctypes.c_int]
+        L.oracle_iou.restype = None
+        L.oracle_iou.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, f32p]
         L.oracle_aligned_overlap.restype = ctypes.c_float
         L.oracle_aligned_overlap.argtypes = [f32p, f32p]
         L.oracle_focal_loss.restype = ctypes.c_double
@@ -95,6 +97,15 @@ def nms(scores, boxes, classes, nms_thresh, detections, rotated=False, fixed_ang
 def rotated_overlap(ibox, mbox, fixed_angle=False):
     a, b = _f32(ibox), _f32(mbox)
     return float(lib().oracle_rotated_overlap(_p(a), _p(b), int(bool(fixed_angle))))
+
+
+def iou(boxes, anchors):
+    """odtk._C.iou restated (oracle_iou): boxes [nb, 8], anchors [na, 8] corner lists -> [na, nb]."""
+    b, a = _f32(boxes).reshape(-1, 8), _f32(anchors).reshape(-1, 8)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().oracle_iou(_p(b), _p(a), b.shape[0], a.shape[0], _p(out))
+    return out
 
 
 def aligned_overlap(ibox, mbox):

@@ -51,4 +51,13 @@ long long ref_nms(int batch, const void *scores, const void *boxes, const void *
   } catch (...) { return -1; }
 }
 
+// odtk::cuda::iou (nms_iou.h:33-35): boxes / anchors as corner lists [n, 4, 2], out [num_anchors, num_boxes]
+long long ref_iou(const void *boxes, const void *anchors, void *out, int num_boxes, int num_anchors, cudaStream_t stream) {
+  const void *inputs[2] = {boxes, anchors};
+  void *outputs[1] = {out};
+  try {
+    return odtk::cuda::iou(inputs, outputs, num_boxes, num_anchors, stream);
+  } catch (...) { return -1; }
+}
+
 }  // extern "C"

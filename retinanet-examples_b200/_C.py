@@ -1,7 +1,7 @@
 """Mirror of the reference's compiled extension module `odtk._C` (csrc/extensions.cpp:184-201):
 `decode`, `nms` with the same signatures, argument meaning, shapes, dtypes and error behaviour
 (RuntimeError on non-CUDA / non-contiguous input, extensions.cpp:42-44), implemented by the
-sm_100a kernels behind the C ABI.  `iou` and `Engine` (TensorRT) are outside the hot path."""
+sm_100a kernels behind the C ABI; `iou` (extensions.cpp:47-67) likewise.  `Engine` (TensorRT) is outside the hot path."""
 import ctypes
 
 import torch
@@ -176,3 +176,17 @@ def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, re
     if return_index:
         res.append(out_index)
     return res
+
+
+def iou(boxes, anchors):
+    """odtk._C.iou (csrc/extensions.cpp:47-67): polygon IoU of rotated boxes against rotated anchors.
+    boxes: flat (or [..., 8]) fp32 CUDA tensor of num_boxes quadrilaterals (4 corners x (x, y)); anchors likewise.
+    Returns [Tensor[num_anchors, num_boxes]] -- a one-element list, as the reference does."""
+    _check_input(boxes, "boxes")
+    _check_input(anchors, "anchors")
+    num_boxes, num_anchors = boxes.numel() // 8, anchors.numel() // 8
+    out = torch.empty((num_anchors, num_boxes), dtype=torch.float32, device=boxes.device)
+    inputs = _lib.ptr_array([boxes.data_ptr(), anchors.data_ptr()])
+    outputs = _lib.ptr_array([out.data_ptr()])
+    _lib.check(_lib.lib().odtk_iou(inputs, outputs, num_boxes, num_anchors, _stream()), "iou")
+    return [out]

@@ -45,6 +45,7 @@ SIGNATURES = {
     "odtk_nms_ex": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_iou": (ctypes.c_int, [_c_vpp, _c_vpp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "odtk_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "odtk_conv_last_plan": (ctypes.c_int, [ctypes.c_void_p]),
     "odtk_conv_map_cache_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
@@ -60,6 +61,9 @@ SIGNATURES = {
                         [ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_smooth_l1_loss": (ctypes.c_longlong, [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_float, ctypes.c_float] +
                             [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_retina_loss": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_void_p]),
     "odtk_snap_to_anchors": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 5 + [_c_f32p, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, ctypes.c_float] + [ctypes.c_void_p] * 5),
     "odtk_preprocess_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [_c_f32p, _c_f32p, ctypes.c_void_p]),
@@ -74,6 +78,13 @@ class Level(ctypes.Structure):
     """odtk_level_t (include/odtk_b200.h)."""
     _fields_ = [("scores", ctypes.c_void_p), ("deltas", ctypes.c_void_p), ("height", ctypes.c_size_t),
                 ("width", ctypes.c_size_t), ("scale", ctypes.c_size_t), ("anchors", _c_f32p)]
+
+
+class LossLevel(ctypes.Structure):
+    """odtk_loss_level_t (include/odtk_b200.h)."""
+    _fields_ = [("cls_logits", ctypes.c_void_p), ("box_pred", ctypes.c_void_p), ("cls_index", ctypes.c_void_p),
+                ("box_target", ctypes.c_void_p), ("cls_grad", ctypes.c_void_p), ("box_grad", ctypes.c_void_p),
+                ("height", ctypes.c_int), ("width", ctypes.c_int)]
 
 
 class ConvPlan(ctypes.Structure):

@@ -135,3 +135,80 @@ def snap_to_anchors(boxes, size, stride, anchors, num_classes, device, anchor_io
     t = boxes.to(device=device, dtype=torch.float32).reshape(1, -1, 5)
     cls_target, box_target, depth, _ = snap_to_anchors_batch(t, (height, width), stride, anchors, num_classes, anchor_ious)
     return cls_target[0], box_target[0], depth[0]
+
+
+# ---- rotated-box target assignment (reference odtk/box.py:80-96,189-252, odtk/utils.py:33-80) ----
+def rotate_boxes(boxes, points=False):
+    """Target boxes (xmin, ymin, width, height, theta) -> (boxes_axis [G, 6] = (x1, y1, x2, y2, sin, cos),
+    boxes_rotated [G, 8] = the four rotated corners ordered tl, tr, br, bl).  Reference: odtk/utils.py:33-80."""
+    th = boxes[:, 4]
+    u = torch.stack([torch.cos(th), torch.sin(th)], dim=1)
+    l = torch.stack([-torch.sin(th), torch.cos(th)], dim=1)
+    R = torch.stack([u, l], dim=1)                                   # [G, 2, 2]
+    if points:
+        cents = torch.stack([(boxes[:, 0] + boxes[:, 2]) / 2, (boxes[:, 1] + boxes[:, 3]) / 2], 1)
+        x0, y0, x1, y1 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    else:
+        cents = torch.stack([boxes[:, 0] + boxes[:, 2] / 2, boxes[:, 1] + boxes[:, 3] / 2], 1)
+        x0, y0, x1, y1 = boxes[:, 0], boxes[:, 1], boxes[:, 0] + boxes[:, 2], boxes[:, 1] + boxes[:, 3]
+    corners = torch.stack([torch.stack([x0, y0], 1), torch.stack([x1, y0], 1), torch.stack([x1, y1], 1),
+                           torch.stack([x0, y1], 1)], dim=1)         # [G, 4, 2]
+    # per box: R @ (corner - centre) + centre (the reference builds the full [G, 2, G] product and takes its diagonal)
+    rot = torch.matmul(R[:, None], (corners - cents[:, None])[..., None])[..., 0] + cents[:, None]
+    boxes_axis = torch.cat([boxes[:, :2], boxes[:, :2] + boxes[:, 2:4] - 1,
+                            torch.sin(boxes[:, -1, None]), torch.cos(boxes[:, -1, None])], 1)
+    return boxes_axis, _order_points(rot).view(-1, 8)
+
+
+def box2delta_rotated(boxes, anchors):
+    """'Convert boxes to deltas from anchors' -- odtk/box.py:80-94."""
+    anchors_wh = anchors[:, 2:4] - anchors[:, :2] + 1
+    anchors_ctr = anchors[:, :2] + 0.5 * anchors_wh
+    boxes_wh = boxes[:, 2:4] - boxes[:, :2] + 1
+    boxes_ctr = boxes[:, :2] + 0.5 * boxes_wh
+    return torch.cat([(boxes_ctr - anchors_ctr) / anchors_wh, torch.log(boxes_wh / anchors_wh),
+                      boxes[:, 4, None], boxes[:, 5, None]], 1)
+
+
+def snap_to_anchors_rotated(boxes, size, stride, anchors, num_classes, device, anchor_ious):
+    """'Snap target boxes (x, y, w, h, a) to anchors' -- odtk/box.py:192-252, same signature and results.
+    boxes [G, 6] (x, y, w, h, theta, class) of ONE image; anchors = (anchors_axis [A, 4], anchors_rotated [A, 8]) from
+    generate_anchors_rotated; size = [W*stride, H*stride].  The A*H*W x G polygon IoUs run on the sm_100a kernel
+    (_C.iou -> odtk_iou); the arg-max / delta / scatter bookkeeping are the reference's own tensor expressions on the
+    device.  Returns (cls_target [A, C, H, W], box_target [A, 6, H, W], depth [A, 1, H, W])."""
+    anchors_axis, anchors_rotated = anchors
+    num_anchors = anchors_rotated.size()[0] if anchors_rotated is not None else 1
+    width, height = int(size[0] / stride), int(size[1] / stride)
+    if boxes.nelement() == 0:
+        return (torch.zeros([num_anchors, num_classes, height, width], device=device),
+                torch.zeros([num_anchors, 6, height, width], device=device),
+                torch.zeros([num_anchors, 1, height, width], device=device))
+    boxes = boxes.to(device=device, dtype=torch.float32)
+    boxes, classes = boxes.split(5, dim=1)
+    boxes_axis, boxes_rotated = rotate_boxes(boxes)
+    anchors_axis = anchors_axis.to(device=device, dtype=torch.float32)
+    anchors_rotated = anchors_rotated.to(device=device, dtype=torch.float32)
+    xs = torch.arange(0, size[0], stride, device=device, dtype=classes.dtype)
+    ys = torch.arange(0, size[1], stride, device=device, dtype=classes.dtype)
+    x, y = torch.meshgrid(xs, ys, indexing="ij")
+    xy_2corners = torch.stack((x, y, x, y), 2).unsqueeze(0)
+    xy_4corners = torch.stack((x, y, x, y, x, y, x, y), 2).unsqueeze(0)
+    anchors_axis = (xy_2corners.to(torch.float) + anchors_axis.view(-1, 1, 1, 4)).contiguous().view(-1, 4)
+    anchors_rotated = (xy_4corners.to(torch.float) + anchors_rotated.view(-1, 1, 1, 8)).contiguous().view(-1, 8)
+    overlap = _C.iou(boxes_rotated.contiguous().view(-1), anchors_rotated.contiguous().view(-1))[0]
+    overlap, indices = overlap.max(1)                                 # best box per anchor
+    box_target = box2delta_rotated(boxes_axis[indices], anchors_axis)
+    box_target = box_target.view(num_anchors, 1, width, height, 6).transpose(1, 4).transpose(2, 3)
+    box_target = box_target.squeeze().contiguous()
+    depth = torch.ones_like(overlap, device=device) * -1
+    depth[overlap < anchor_ious[0]] = 0                               # background
+    depth[overlap >= anchor_ious[1]] = classes[indices][overlap >= anchor_ious[1]].squeeze() + 1   # objects
+    depth = depth.view(num_anchors, width, height).transpose(1, 2).contiguous()
+    cls_target = torch.zeros((anchors_axis.size()[0], num_classes + 1), device=device, dtype=boxes_axis.dtype)
+    classes = classes[indices].long().view(-1, 1)
+    classes[overlap < anchor_ious[0]] = num_classes                   # background has no class
+    cls_target.scatter_(1, classes, 1)
+    cls_target = cls_target[:, :num_classes].view(-1, 1, width, height, num_classes)
+    cls_target = cls_target.transpose(1, 4).transpose(2, 3).squeeze().contiguous()
+    return (cls_target.view(num_anchors, num_classes, height, width), box_target.view(num_anchors, 6, height, width),
+            depth.view(num_anchors, 1, height, width))

@@ -363,6 +363,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (p.res_pipe) {
+          // residual add as BN / 64 extra K blocks through the ordinary pipeline stages: A slot <- residual chunk
+          // [128 pixels x 64 channels] (same box as an activation block), B slot <- the 64 x 64 identity (8 KB, L2-resident
+          // constant): D[:, 64 j .. 64 j + 63] += R_j * I^T on the tensor core (N = 64 MMAs).  Unlike res_mma no shared
+          // memory is reserved, so the layer keeps all its pipeline stages (4 at BN = 256 instead of 2).
+          for (int j = 0; j < (p.BN >> 6); j++) {
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            unsigned char *sa = smem + stage * kStageBytes;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + 8192u);
+              tma_load_2d(sa, &tmRes, &bars->full[stage], n0 + 64 * j, m_tile * 128);
+              tma_load_2d(sa + kABytes, &tmIdent, &bars->full[stage], 0, 0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
         if (p.res_mma) {
           // residual tile [128 pixels x 256 channels] as four 128B-swizzled 64-channel slices: it becomes the
           // MN-major B operand of D += I * R (identity times residual), i.e. the tensor core does the add
@@ -533,6 +549,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (p.res_pipe) {
+          const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 64
+          for (int j = 0; j < (p.BN >> 6); j++) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+            const uint64_t da = make_desc_kmajor(sa, 128), db = make_desc_kmajor(sa + kABytes, 128);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+              tc_commit(&bars->empty[stage]);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
         if (p.res_mma) {
           mbar_wait(&bars->res_full, rphase);
           tc_fence_after();
@@ -588,7 +619,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = lane >> lsh, lx = lane & (lpr - 1);
     const int nsegs = (nchunks + cpw - 1) / cpw;
     const bool nhwc = p.out_mode == ODTK_OUT_NHWC_F16;
-    const bool has_addend = (p.residual != nullptr && !p.res_mma) || (UPS && p.upsample != nullptr);
+    const bool has_addend = (p.residual != nullptr && !p.res_mma && !p.res_pipe) || (UPS && p.upsample != nullptr);
     const int hw = p.H * p.W, per_img = p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
     // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
     int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
@@ -645,7 +676,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < 8; k++) {
             dst[k] = make_uint4(0u, 0u, 0u, 0u);
             if (pix8[k] >= 0 && lane_on) {
-              if (p.residual && !p.res_mma) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
+              if (p.residual && !p.res_mma && !p.res_pipe) dst[k] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (long long)pix8[k] * p.ldr + colbase));
               if (UPS && p.upsample) {
                 const int i2 = pix8[k] / hw, rem = pix8[k] - i2 * hw, h2 = rem / p.W, w2 = rem - h2 * p.W;
                 const long long up = ((long long)i2 * p.up_h + (h2 >> 1)) * p.up_w + (w2 >> 1);
@@ -1012,8 +1043,10 @@ void launch_conv(int grid, cudaStream_t stream, const CUtensorMap &tmA, const CU
 // block: 128 rows x 64 fp16, columns 0 and 1 are 1.0).  __device__ globals: one instance per device.
 __device__ __half g_ident_op[128 * 128];
 __device__ __half g_upsel_op[128 * 64];   // U[i][k] = (k == i >> 1): nearest-upsample selection (A operand of the FPN add)
+__device__ __half g_ident64_op[64 * 64];   // 64 x 64 identity: B operand of the pipelined residual add
 __device__ __half g_ones_op[128 * 64];
 __global__ void init_const_operands_kernel() {
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) g_ident64_op[i] = __float2half_rn((i >> 6) == (i & 63) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_upsel_op[i] = __float2half_rn((i & 63) == (i >> 7) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) g_ident_op[i] = __float2half_rn((i >> 7) == (i & 127) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) g_ones_op[i] = __float2half_rn((i & 63) < 2 ? 1.0f : 0.0f);
@@ -1040,7 +1073,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready;
   int num_sms;
-  void *ident, *ones, *upsel;
+  void *ident, *ones, *upsel, *ident64;
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_dev_mu;
@@ -1054,7 +1087,8 @@ const DeviceState *device_state(cudaStream_t stream) {
   if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.num_sms <= 0) return nullptr;
   if (!configure_kernels()) return nullptr;
   if (cudaGetSymbolAddress(&d.ident, g_ident_op) != cudaSuccess || cudaGetSymbolAddress(&d.ones, g_ones_op) != cudaSuccess ||
-      cudaGetSymbolAddress(&d.upsel, g_upsel_op) != cudaSuccess) return nullptr;
+      cudaGetSymbolAddress(&d.upsel, g_upsel_op) != cudaSuccess ||
+      cudaGetSymbolAddress(&d.ident64, g_ident64_op) != cudaSuccess) return nullptr;
   init_const_operands_kernel<<<1, 256, 0, stream>>>();
   if (cudaGetLastError() != cudaSuccess) return nullptr;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1214,7 +1248,8 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     // row-major tiles keep the fp32 NCHW stores of the head outputs in 32-byte runs: prefer them there
     const bool transposed = (p.out_mode == ODTK_OUT_NHWC_F16) ? eff_b > eff_a + 1e-9 : eff_b > 1.15 * eff_a;
     const double eff_halo = transposed ? eff_b : eff_a;
-    if (halo_on && eff_halo >= 0.84 * eff_free && d->h >= 8 && d->width >= 8) {
+    // narrow N (head outputs with few channels): the per-tap A re-load of mode 1 dominates, take the halo tiles anyway
+    if (halo_on && (eff_halo >= 0.84 * eff_free || (BN <= 64 && eff_halo >= 0.6 * eff_free)) && d->h >= 8 && d->width >= 8) {
       p.mode = 4;
       p.tile_t = transposed ? 1 : 0;
       p.halo_boff = halo_boff;
@@ -1268,7 +1303,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (cluster_res < 0) { const char *e = getenv("ODTK_CONV_CLUSTER_RES"); cluster_res = e ? atoi(e) : 0; }   // 1x1 + residual layers as multicast pairs (weights read once per pair from L2)
   const bool res_pair = cluster_res && d->residual && d->ksize == 1 && stride == 1 && BN == 256 && d->cout % 256 == 0;
   static int two_narrow = -1;
-  if (two_narrow < 0) { const char *e = getenv("ODTK_CONV_TWO_NARROW"); two_narrow = e ? atoi(e) : 0; }   // cta_group::2 pairs for narrow fp32-output head layers (halved weight stream per CTA)
+  if (two_narrow < 0) { const char *e = getenv("ODTK_CONV_TWO_NARROW"); two_narrow = e ? atoi(e) : 1; }   // cta_group::2 pairs for narrow fp32-output head layers (halved weight stream per CTA)
   const bool narrow_pair = two_narrow && cluster_on >= 2 && p.mode == 4 && p.out_mode != ODTK_OUT_NHWC_F16 && BN >= 32 && BN <= 128;
   if (cluster_on && (BN > 128 || narrow_pair) && !d->upsample && (!d->residual || res_pair) && (cluster_1x1 || d->ksize == 3 || res_pair) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
@@ -1291,9 +1326,20 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   }
   // residual add on the tensor core (D += I * R): wide 1x1 residual layers (bottleneck conv3)
   CUtensorMap tmRes = tmB, tmIdent = tmB;
+  static int res_pipe_on = -1;
+  if (res_pipe_on < 0) { const char *e = getenv("ODTK_CONV_RES_PIPE"); res_pipe_on = e ? atoi(e) : 1; }
+  if (res_pipe_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && !p.cluster2 && (BN % 64) == 0 &&
+      d->cout % 64 == 0 && (p.ldr % 8) == 0 && (((uintptr_t)d->residual) & 15) == 0) {
+    uint64_t dimsR[2] = {(uint64_t)p.ldr, (uint64_t)p.M}, strR[1] = {(uint64_t)p.ldr * 2};
+    uint32_t boxR[2] = {64, 128};
+    uint64_t dimsI[2] = {64, 64}, strI[1] = {128};
+    uint32_t boxI[2] = {64, 64};
+    if (encode_map(&tmRes, d->residual, 2, dimsR, strR, boxR) && encode_map(&tmIdent, dstate->ident64, 2, dimsI, strI, boxI))
+      p.res_pipe = 1;
+  }
   static int res_mma_on = -1;
   if (res_mma_on < 0) { const char *e = getenv("ODTK_CONV_RES_MMA"); res_mma_on = e ? atoi(e) : 1; }
-  if (res_mma_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN == 256 && d->cout % 256 == 0 &&
+  if (res_mma_on && !p.res_pipe && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN == 256 && d->cout % 256 == 0 &&
       (p.ldr % 8) == 0 && (((uintptr_t)d->residual) & 15) == 0) {
     const void *ident = dstate->ident;
     uint64_t dimsR[2] = {(uint64_t)p.ldr, (uint64_t)p.M}, strR[1] = {(uint64_t)p.ldr * 2};
@@ -1343,7 +1389,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   g_last_plan = odtk_conv_plan_t{p.mode, p.cluster2, p.BN, p.num_m_tiles, p.num_n_tiles, p.nstages, p.npatch, p.tile_t,
-                                 p.b_resident, p.bias_mma, p.res_mma, p.tma_store, p.TH, p.TW, grid, p.up_mma};
+                                 p.b_resident, p.bias_mma, p.res_mma + 2 * p.res_pipe, p.tma_store, p.TH, p.TW, grid, p.up_mma};
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
     launch_conv(grid, stream, tmA, tmB, tmC, tmOnes, tmBias, tmRes, tmIdent, p);

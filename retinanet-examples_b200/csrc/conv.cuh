@@ -18,6 +18,7 @@ struct ConvParams {
   int row_bytes;        // bytes of one K block row in shared memory: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, stem)
   int cluster2;         // launched as 2-CTA clusters: each CTA loads half of the weight tile and multicasts it
   int res_mma;          // the residual is added by the tensor core: D += I * R (mode 0, BN = 256)
+  int res_pipe;         // the residual is added as BN / 64 extra K blocks (A = residual chunk, B = 64 x 64 identity, N = 64 MMAs)
   int bias_mma;         // the bias is added by one extra K block on the tensor core (A = ones, B = bias hi/lo)
   int tma_store;        // epilogue hands 32x64 slabs to cp.async.bulk.tensor stores (mode 0, BN > 128)
   int nstages;          // pipeline stages that fit: (16 KB + BN*128 B) each

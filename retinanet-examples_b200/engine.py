@@ -213,12 +213,17 @@ def stem_pool_padded(xp, h, wd, w, bias, cout, relu=True):
     return out
 
 
-def stem_pool(x, w, bias, cout, relu=True):
-    """NHWC fp16 RGB batch [N,H,W,3] -> zero-pad to NHWC4 (one small kernel) -> fused stem + max-pool."""
+def pad_input(x):
+    """NHWC fp16 RGB batch [N,H,W,3] -> zero-bordered NHWC4 [N, H+6, W+8, 4] (the stem kernels' input layout)."""
     n, h, wd, c = x.shape
     assert c == 3 and x.dtype == torch.float16 and x.is_contiguous()
     xp = torch.empty((n, h + 6, wd + 8, 4), dtype=torch.float16, device=x.device)
     _lib.check(_lib.lib().odtk_pad_input(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(xp.data_ptr()), n, h, wd, _stream()), "pad_input")
     STATS["launches"] += 1
     _trace("pad_input", 0, x.numel() * 2 + xp.numel() * 2, n=n, h=h, w=wd, cin=3)
-    return stem_pool_padded(xp, h, wd, w, bias, cout, relu)
+    return xp
+
+
+def stem_pool(x, w, bias, cout, relu=True):
+    """NHWC fp16 RGB batch [N,H,W,3] -> zero-pad to NHWC4 (one small kernel) -> fused stem + max-pool."""
+    return stem_pool_padded(pad_input(x), x.shape[1], x.shape[2], w, bias, cout, relu)

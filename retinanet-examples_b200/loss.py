@@ -120,3 +120,47 @@ def smooth_l1_loss_sum(pred, target, mask=None, beta=0.11):
     """sum(mask * SmoothL1Loss(pred, target)) with its gradient in the same pass
     (== `(box_mask * box_criterion(box_head, box_target)).sum()`, odtk/model.py:201-205)."""
     return _L1Sum.apply(pred, target, mask, beta)
+
+
+def retina_loss(cls_heads, box_heads, cls_indices, box_targets, num_classes, alpha=0.25, gamma=2.0, beta=0.11,
+                with_grad=False):
+    """Model._compute_loss (odtk/model.py:186-210) for ALL pyramid levels in ONE kernel launch (odtk_retina_loss):
+    cls_heads[l] [B, A*C, H, W] raw logits, box_heads[l] [B, A*nbox, H, W], cls_indices[l] [B, A, H, W] int32 (class,
+    -1 background, -2 ignored: box.snap_to_anchors_batch), box_targets[l] [B, A, nbox, H, W].
+    Returns (cls_loss, box_loss) 0-dim tensors, both already divided by sum_l max(1, #foreground_l); with_grad=True also
+    returns (cls_grads, box_grads): d cls_loss / d cls_heads[l] and d box_loss / d box_heads[l]."""
+    nl = len(cls_heads)
+    if not (nl == len(box_heads) == len(cls_indices) == len(box_targets)) or nl == 0:
+        raise ValueError("one entry per pyramid level in every list")
+    dev = cls_heads[0].device
+    if not cls_heads[0].is_cuda:
+        raise RuntimeError("retina_loss needs CUDA tensors: there is no CPU path")
+    batch = cls_heads[0].shape[0]
+    num_anchors = cls_indices[0].shape[1]
+    nbox = box_targets[0].shape[2]
+    keep, levels = [], (_lib.LossLevel * nl)()
+    cls_grads, box_grads = [], []
+    for l in range(nl):
+        c, b = cls_heads[l].float().contiguous(), box_heads[l].float().contiguous()
+        ci, bt = cls_indices[l].int().contiguous(), box_targets[l].float().contiguous()
+        if c.shape[1] != num_anchors * num_classes or b.shape[1] != num_anchors * nbox or tuple(ci.shape[2:]) != tuple(c.shape[2:]):
+            raise ValueError("level %d: head / target shapes do not agree" % l)
+        keep += [c, b, ci, bt]
+        levels[l].cls_logits, levels[l].box_pred = c.data_ptr(), b.data_ptr()
+        levels[l].cls_index, levels[l].box_target = ci.data_ptr(), bt.data_ptr()
+        if with_grad:
+            cls_grads.append(torch.empty_like(c))
+            box_grads.append(torch.empty_like(b))
+            levels[l].cls_grad, levels[l].box_grad = cls_grads[-1].data_ptr(), box_grads[-1].data_ptr()
+        levels[l].height, levels[l].width = c.shape[2], c.shape[3]
+    out = torch.empty(4, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    args = (batch, nl, ctypes.cast(levels, ctypes.c_void_p), int(num_anchors), int(num_classes), int(nbox), float(alpha),
+            float(gamma), float(beta), ctypes.c_void_p(out.data_ptr()))
+    size = _lib.check(L.odtk_retina_loss(*args, None, 0, None), "retina_loss (workspace query)")
+    ws = torch.empty(int(size), dtype=torch.uint8, device=dev)
+    _lib.check(L.odtk_retina_loss(*args, ctypes.c_void_p(ws.data_ptr()), size,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "retina_loss")
+    if with_grad:
+        return out[0], out[1], cls_grads, box_grads
+    return out[0], out[1]

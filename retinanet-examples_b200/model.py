@@ -1,7 +1,8 @@
 """RetinaNet inference model -- host-side mirror of the reference's odtk/model.py `Model`
 (constructor arguments, `config` keys, state_dict key names, `forward(x) -> (scores, boxes,
 classes)`), executing on the sm_100a kernels behind the C ABI instead of nn.Conv2d/cuDNN +
-odtk._C.  Training (`_compute_loss`), checkpoint files and ONNX/TensorRT export are outside the
+odtk._C.  `_compute_loss` (training-mode forward) runs target assignment + ONE fused loss kernel; `save` / `load` /
+`initialize(pre_trained)` read and write the reference's checkpoint dict; ONNX/TensorRT export is outside the
 hot path; `load_state_dict` ingests exactly the reference's key layout
 (odtk/model.py:217-258): `backbones.<Name>.features.*`, `backbones.<Name>.{lateral,pyramid,smooth}*`,
 `cls_head.{0,2,4,6,8}.*`, `box_head.{0,2,4,6,8}.*`.
@@ -140,6 +141,7 @@ class Model:
         self.backbone = backbones
         self.name = 'RetinaNet'
         self.exporting = False
+        self.training = False
         self.rotated_bbox = rotated_bbox
         self.anchor_ious = anchor_ious
         self.ratios, self.scales = ratios, scales
@@ -151,6 +153,10 @@ class Model:
         self.nms = config.get('nms', 0.5)
         self.detections = config.get('detections', 100)
         self.stride = 128
+        if self.top_n > 4096 or self.detections > 1024 or 5 * self.top_n > 6144:
+            raise ValueError("config outside the sm_100a kernels' limits (include/odtk_b200.h): top_n <= 4096, "
+                             "5 * top_n <= 6144 candidates per image into NMS, detections <= 1024; got top_n=%d detections=%d"
+                             % (self.top_n, self.detections))
         self.num_anchors = len(ratios) * len(scales) * (len(self.angles) if rotated_bbox else 1)
         self._sd = None
         self._packed = None
@@ -167,11 +173,45 @@ class Model:
 
     # ---- weights ---------------------------------------------------------------------------------
     def initialize(self, pre_trained=None, seed=0):
-        """Random init (reference: odtk/model.py:79-123; pre-trained checkpoints are unavailable)."""
+        """Reference odtk/model.py:79-123.  `pre_trained`: a checkpoint file written by `save` (or by the reference):
+        every weight except the class head's last layer (and, rotated, the box head's) is taken from it -- fine-tuning, as
+        the reference does; those layers get the prior initialisation.  Otherwise seeded random init (no ImageNet
+        backbone checkpoints exist offline)."""
+        sd = make_state_dict(self.backbone, self.classes, self.num_anchors, self.rotated_bbox, seed)
         if pre_trained:
-            raise ValueError("checkpoint files are outside the hot path; use load_state_dict()")
-        self.load_state_dict(make_state_dict(self.backbone, self.classes, self.num_anchors, self.rotated_bbox, seed))
+            if not os.path.isfile(pre_trained):
+                raise ValueError('No checkpoint {}'.format(pre_trained))
+            chk = torch.load(pre_trained, map_location="cpu", weights_only=False)
+            ignored = ['cls_head.8.bias', 'cls_head.8.weight']
+            if self.rotated_bbox:
+                ignored += ['box_head.8.bias', 'box_head.8.weight']
+            sd.update({k: v for k, v in chk['state_dict'].items() if k not in ignored and k in sd})
+        self.load_state_dict(sd)
         return self
+
+    # ---- checkpoint files (reference odtk/model.py:217-258: same dict layout, readable by either side) ---------
+    def save(self, state):
+        checkpoint = {'backbone': [self.backbone], 'classes': self.classes, 'state_dict': self.state_dict(),
+                      'ratios': self.ratios, 'scales': self.scales}
+        if self.rotated_bbox and self.angles:
+            checkpoint['angles'] = self.angles
+        for key in ('iteration', 'optimizer', 'scheduler'):
+            if key in state:
+                checkpoint[key] = state[key]
+        torch.save(checkpoint, state['path'])
+
+    @classmethod
+    def load(cls, filename, rotated_bbox=False):
+        if not os.path.isfile(filename):
+            raise ValueError('No checkpoint {}'.format(filename))
+        checkpoint = torch.load(filename, map_location="cpu", weights_only=False)
+        kwargs = {k: checkpoint[k] for k in ('ratios', 'scales', 'angles') if k in checkpoint}
+        if ('angles' in checkpoint) or rotated_bbox:
+            kwargs['rotated_bbox'] = True
+        model = cls(backbones=checkpoint['backbone'], classes=checkpoint['classes'], **kwargs)
+        model.load_state_dict(checkpoint['state_dict'])
+        state = {key: checkpoint[key] for key in ('iteration', 'optimizer', 'scheduler') if key in checkpoint}
+        return model, state
 
     def state_dict(self):
         return self._sd
@@ -197,6 +237,15 @@ class Model:
         return self
 
     def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        """Training-mode forward (odtk/model.py:130-138): `model([images, targets])` returns (cls_loss, box_loss).  The
+        convolutions have no backward kernels here (the training loop is outside the hot path): the
+        losses and -- `_compute_loss(..., with_grad=True)` -- their gradients w.r.t. the head outputs are what this
+        provides."""
+        self.training = bool(mode)
         return self
 
     def share_memory(self):
@@ -389,7 +438,51 @@ class Model:
         _, box_heads = self._heads(features, True, sinks)
         return tuple(_C.nms(*fd.finish(box_heads), self.nms, self.detections, self.rotated_bbox))
 
+    # ---- training-side losses (reference odtk/model.py:167-210) ---------------------------------------------------
+    def _extract_targets(self, targets, stride, size):
+        """Per level: class-index targets [B, A, H, W] int32, box targets [B, A, nbox, H, W], depth [B, A, 1, H, W].
+        Axis-aligned: the whole batch in one launch (odtk_snap_to_anchors); rotated: per image, polygon IoUs on
+        odtk_iou (odtk/model.py:167-184)."""
+        if stride not in self.anchors:
+            self.anchors[stride] = (box.generate_anchors_rotated(stride, self.ratios, self.scales, self.angles)
+                                    if self.rotated_bbox else box.generate_anchors(stride, self.ratios, self.scales))
+        anchors = self.anchors[stride]
+        h, w = int(size[0]), int(size[1])
+        if not self.rotated_bbox:
+            _, box_target, depth, cls_index = box.snap_to_anchors_batch(targets, (h, w), stride, anchors, self.classes,
+                                                                        self.anchor_ious, dense=False)
+            return cls_index, box_target, depth
+        bts, dps = [], []
+        for target in targets:
+            target = target[target[:, -1] > -1]
+            _, bt, dp = box.snap_to_anchors_rotated(target, [w * stride, h * stride], stride, anchors, self.classes,
+                                                    targets.device, self.anchor_ious)
+            bts.append(bt)
+            dps.append(dp)
+        box_target, depth = torch.stack(bts), torch.stack(dps)
+        d = depth[:, :, 0]
+        cls_index = torch.where(d > 0, d - 1, torch.where(d == 0, torch.full_like(d, -1), torch.full_like(d, -2))).int()
+        return cls_index.contiguous(), box_target, depth
+
+    def _compute_loss(self, x, cls_heads, box_heads, targets, with_grad=False):
+        """odtk/model.py:186-210: target assignment per level, then ONE fused launch for the focal + smooth-L1 losses of
+        all levels, the masks, the foreground counts and the normalisation (loss.retina_loss -> odtk_retina_loss)."""
+        from . import loss as loss_mod
+        width = x.shape[-1] if torch.is_tensor(x) else int(x)
+        cls_idx, box_tgt = [], []
+        for cls_head in cls_heads:
+            size = cls_head.shape[-2:]
+            stride = width // cls_head.shape[-1]
+            ci, bt, _ = self._extract_targets(targets, stride, size)
+            cls_idx.append(ci)
+            box_tgt.append(bt)
+        return loss_mod.retina_loss(cls_heads, box_heads, cls_idx, box_tgt, self.classes, with_grad=with_grad)
+
     def forward(self, x, rotated_bbox=None):
+        if self.training:
+            x, targets = x
+            cls_heads, box_heads = self.forward_heads(x, sigmoid=False)
+            return self._compute_loss(x, cls_heads, box_heads, targets.float().to(cls_heads[0].device))
         if self.fused_candidates and not self.exporting:
             return self._forward_fused(x)
         if x.dtype == torch.uint8:                       # raw HWC images: fused input side
@@ -434,6 +527,6 @@ class Model:
         return static_out
 
     def __call__(self, x, rotated_bbox=None, static_input=False):
-        if getattr(self, "_graphs", None) is not None and not self.exporting:
+        if getattr(self, "_graphs", None) is not None and not self.exporting and not self.training:
             return self._forward_graphed(x, rotated_bbox, static_input)
         return self.forward(x, rotated_bbox)

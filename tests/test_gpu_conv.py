@@ -256,10 +256,12 @@ def test_relu_copy():
 @pytest.mark.parametrize("shape,ks,kw,expect", [
     ((4, 100, 160, 256, 256), 3, {}, {"mode": 4, "cluster": 2, "bn": 256}),               # halo, cta_group::2 pairs
     ((2, 200, 320, 64, 64), 3, {}, {"mode": 4, "b_resident": 1, "bn": 64}),               # resident weights
-    ((2, 50, 80, 256, 1024), 1, {"residual": True}, {"mode": 0, "res_mma": 1, "bn": 256}),  # residual on the tensor core
+    ((2, 50, 80, 256, 1024), 1, {"residual": True}, {"mode": 0, "res_mma": 2, "bn": 256, "nstages": 4}),  # residual chunks through the pipeline (R_j * I64)
     ((2, 200, 320, 256, 64), 1, {}, {"mode": 0, "bn": 64}),
     ((2, 100, 160, 512, 1024), 1, {"stride": 2}, {"mode": 3}),                             # even stride 2: parity split
-    ((32, 7, 10, 256, 256), 3, {}, {"mode": 4, "bn": 128}),                                # few tiles: narrower N tile
+    ((32, 7, 10, 256, 256), 3, {}, {"mode": 1, "bn": 128}),                                # few tiles: narrower N tile
+    ((2, 100, 160, 128, 512), 1, {"residual": True}, {"mode": 0, "res_mma": 2}),
+    ((1, 100, 160, 256, 36), 3, {"f32": True}, {"mode": 4, "cluster": 2, "bn": 48}),           # narrow head output: cta_group::2 pairs
 ])
 def test_conv_variant_selection(shape, ks, kw, expect):
     """The host code picks the kernel variant from the shape; assert which one ran AND that it is right."""
@@ -269,12 +271,18 @@ def test_conv_variant_selection(shape, ks, kw, expect):
     stride = kw.get("stride", 1)
     res = _rand((n, h, w, cout), g) if kw.get("residual") else None
     bd = b.to(DEV)
-    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=True,
-                      residual=res.to(DEV) if res is not None else None, stride=stride, bias_op=engine.pack_bias(bd))
+    f32 = kw.get("f32", False)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, cout, ks, relu=not f32,
+                      residual=res.to(DEV) if res is not None else None, stride=stride, bias_op=engine.pack_bias(bd),
+                      out_mode=engine.OUT_NCHW_F32 if f32 else engine.OUT_NHWC_F16)
     plan = engine.last_plan()
     for k, v in expect.items():
         assert plan[k] == v, (k, plan)
-    _close16(y, _ref_conv(x, wt, b, ks, relu=True, residual=res, stride=stride, pad=ks // 2))
+    if f32:
+        ref = _ref_conv(x, wt, b, ks)
+        assert (y.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    else:
+        _close16(y, _ref_conv(x, wt, b, ks, relu=True, residual=res, stride=stride, pad=ks // 2))
 
 
 def test_tensor_map_cache_hits_on_repeated_calls():

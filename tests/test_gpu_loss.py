@@ -77,3 +77,40 @@ def test_smooth_l1_matches_reference_golden_and_oracle(golden_dir):
     l2.backward()
     np.testing.assert_allclose(float(l2), tot, rtol=1e-5)
     np.testing.assert_allclose(p2.grad.cpu().numpy().reshape(-1), gr, rtol=1e-5, atol=1e-6)
+
+
+def test_compute_loss_one_launch_matches_reference_golden(golden_dir):
+    """Model._compute_loss (odtk/model.py:186-210) of the UNMODIFIED reference on seeded heads / targets
+    (tests/golden/compute_loss.npz, oracle/gen_golden_loss.py) == target assignment + ONE fused launch here:
+    both normalised losses (rtol 2e-5) and the gradients autograd produced for every head tensor."""
+    import os
+    from retinanet_examples_b200.model import Model
+    g = np.load(os.path.join(golden_dir, "compute_loss.npz"))
+    classes = int(g["classes"])
+    model = Model("ResNet18FPN", classes=classes)
+    cls_heads = [torch.from_numpy(g["cls%d" % i]).to(DEV) for i in range(5)]
+    box_heads = [torch.from_numpy(g["box%d" % i]).to(DEV) for i in range(5)]
+    targets = torch.from_numpy(g["targets"]).to(DEV)
+    cls_loss, box_loss, cg, bg = model._compute_loss(int(g["width"]), cls_heads, box_heads, targets, with_grad=True)
+    np.testing.assert_allclose(float(cls_loss), float(g["cls_loss"]), rtol=2e-5)
+    np.testing.assert_allclose(float(box_loss), float(g["box_loss"]), rtol=2e-5)
+    for i in range(5):
+        np.testing.assert_allclose(cg[i].cpu().numpy(), g["cls_grad%d" % i], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(bg[i].cpu().numpy(), g["box_grad%d" % i], rtol=2e-4, atol=1e-7)
+    # deterministic: bit-identical on a second run
+    c2, b2 = model._compute_loss(int(g["width"]), cls_heads, box_heads, targets)
+    assert float(c2) == float(cls_loss) and float(b2) == float(box_loss)
+
+
+def test_training_mode_forward_returns_losses():
+    """model.train(); model([images, targets]) -> (cls_loss, box_loss), as odtk/model.py:130-138."""
+    from retinanet_examples_b200.model import Model, make_state_dict
+    classes = 4
+    model = Model("ResNet18FPN", classes=classes).load_state_dict(make_state_dict("ResNet18FPN", classes, 9, False, seed=2)).cuda(0)
+    x = torch.randn((2, 3, 128, 256), generator=torch.Generator().manual_seed(1)).to(DEV)
+    t = torch.tensor([[[20., 30., 60., 40., 1.], [100., 10., 50., 90., 3.]], [[5., 5., 100., 100., 0.], [-1., -1., -1., -1., -1.]]]).to(DEV)
+    cls_loss, box_loss = model.train()([x, t])
+    assert torch.isfinite(cls_loss) and torch.isfinite(box_loss) and float(cls_loss) > 0 and float(box_loss) > 0
+    model.eval()
+    s, b, c = model(x)
+    assert s.shape == (2, 100)

@@ -156,3 +156,22 @@ def test_snap_to_anchors_oracle_matches_reference(golden_dir):
         np.testing.assert_array_equal(ci >= 0, d > 0)
         np.testing.assert_array_equal(ci == -2, d == -1)
         np.testing.assert_array_equal(ci[ci >= 0], d[d > 0].astype(np.int32) - 1)
+
+
+def test_oracle_iou_matches_golden_and_reference_rotated_snap(golden_dir):
+    """oracle_iou (restated nms_iou.cu:324-387) against the committed known answers, and the host-side mirrors of
+    odtk.utils.rotate_boxes / odtk.box.box2delta_rotated against what the unmodified reference produced
+    (tests/golden/snap_rotated.npz, oracle/gen_golden_rotated.py)."""
+    import torch
+    from oracle import oracle
+    from retinanet_examples_b200 import box
+    g = np.load(os.path.join(golden_dir, "snap_rotated.npz"))
+    np.testing.assert_array_equal(oracle.iou(g["iou_boxes"], g["iou_anchors"]), g["iou"])
+    for k in range(int(g["ncases"])):
+        b = torch.from_numpy(g["c%d_boxes" % k])
+        axis, rot = box.rotate_boxes(b[:, :5])
+        np.testing.assert_allclose(axis.numpy(), g["c%d_boxes_axis" % k], rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(rot.numpy(), g["c%d_boxes_rot" % k], rtol=1e-6, atol=2e-4)
+        aa = torch.from_numpy(g["c%d_anchors_axis" % k])
+        d = box.box2delta_rotated(axis[:1].expand(aa.shape[0], 6), aa)
+        assert d.shape == (aa.shape[0], 6) and torch.isfinite(d).all()
