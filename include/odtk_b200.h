@@ -143,6 +143,31 @@ long long odtk_nms_ex(int batch, const void *const *inputs, void *const *outputs
                       int32_t *out_index, void *workspace, size_t workspace_size,
                       odtk_stream_t stream);
 
+/* nms + gather (B200-native).  As odtk_nms_ex, plus:
+ *   packed (device [B, D, 2 + nbox] fp32, may be NULL): the detections as (score, box..., class) rows -- the layout that
+ *     travels between ranks; outputs may then be NULL.
+ *   gather (may be NULL): image-wise sharded inference (odtk/infer.py:98-102 all_gathers the per-rank results).  Here
+ *     the NMS kernel itself stores each image's packed rows into EVERY rank's gather buffer through NVLink peer
+ *     mappings and counts its arrival there; odtk_gather_wait (same stream, after the call) returns once all ranks'
+ *     rows of the current step have landed in THIS rank's buffer.  No NCCL launch, nothing between the kernels: the
+ *     whole step, collective included, is CUDA-graph capturable.
+ *     packed[p]: rank p's gather buffer (peer-mapped device pointer; packed[rank] is the local one), two parity
+ *     halves of [num_peers * B, D, 2 + nbox] fp32 (step k lands in half k & 1, so a rank that runs ahead never
+ *     overwrites rows its neighbour is still reading); flags[p]: rank p's arrival counters, uint32[num_peers],
+ *     zero-initialised once; epoch: LOCAL device uint32 step counter, zero-initialised, advanced by odtk_gather_wait. */
+#define ODTK_MAX_PEERS 8
+typedef struct {
+  void *packed[ODTK_MAX_PEERS];
+  unsigned *flags[ODTK_MAX_PEERS];
+  unsigned *epoch;
+  int num_peers, rank;
+} odtk_gather_t;
+long long odtk_nms_gather(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                          int detections_per_im, float nms_thresh, int nbox, int fixed_angle, int32_t *out_index,
+                          void *packed, const odtk_gather_t *gather, void *workspace, size_t workspace_size,
+                          odtk_stream_t stream);
+int odtk_gather_wait(const odtk_gather_t *gather, int batch, odtk_stream_t stream);
+
 /* ---- iou (rotated target assignment) ---------------------------
  * Replaces odtk::cuda::iou (csrc/cuda/nms_iou.h:33-35, nms_iou.cu:324-387), the kernel behind
  * odtk._C.iou (csrc/extensions.cpp:47-67,200).

@@ -30,10 +30,35 @@ def _conv(sd, p, x, stride=1, padding=0):
     return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
 
 
-def features(sd, backbone, x):
+# ---- fp16-emulating mode ------------------------------------------------------------------------------------------
+# The product path stores activations and weights in fp16 and accumulates in fp32 (what "fp16" means for the reference
+# too: apex AMP O2 / a TensorRT FP16 engine).  With fp16=True this oracle performs the SAME
+# roundings -- BatchNorm folded into the weights in fp32, weights rounded to fp16 once, every layer's output (after bias,
+# residual / upsample add and ReLU, all in fp32) rounded to fp16, head outputs kept in fp32 -- so that what remains
+# between it and the CUDA path is fp32 summation order (plus the rare 1-ulp fp16 rounding flip it causes): the conv
+# stack can then be held to 2e-3 * max|ref| and detections to 1e-3 instead of the 3e-2 an all-fp32 oracle allows.
+def _q(x, fp16):
+    return x.half().float() if fp16 else x
+
+
+def _cb(sd, pconv, pbn, x, stride=1, padding=0, fp16=False):
+    """conv (+ eval BatchNorm).  fp16: folded weights rounded to fp16, fp32 accumulation, fp32 shift added after."""
+    if not fp16:
+        y = _conv(sd, pconv, x, stride, padding)
+        return _bn(sd, pbn, y) if pbn else y
+    w, b = sd[pconv + ".weight"], sd.get(pconv + ".bias")
+    if pbn:
+        scale = sd[pbn + ".weight"] / torch.sqrt(sd[pbn + ".running_var"] + 1e-5)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = sd[pbn + ".bias"] - sd[pbn + ".running_mean"] * scale
+    return F.conv2d(x, w.half().float(), b, stride=stride, padding=padding)
+
+
+def features(sd, backbone, x, fp16=False):
     block, layers = LAYERS[backbone]
     f = "backbones.%s.features." % backbone
-    x = F.relu(_bn(sd, f + "bn1", _conv(sd, f + "conv1", x, 2, 3)))
+    x = _q(x, fp16)
+    x = _q(F.relu(_cb(sd, f + "conv1", f + "bn1", x, 2, 3, fp16)), fp16)
     x = F.max_pool2d(x, 3, 2, 1)
     outs = []
     for li, nblocks in enumerate(layers):
@@ -42,40 +67,42 @@ def features(sd, backbone, x):
             p = f + "layer%d.%d." % (li + 1, b)
             identity = x
             if block == "bottleneck":
-                out = F.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x)))
-                out = F.relu(_bn(sd, p + "bn2", _conv(sd, p + "conv2", out, stride, 1)))
-                out = _bn(sd, p + "bn3", _conv(sd, p + "conv3", out))
+                out = _q(F.relu(_cb(sd, p + "conv1", p + "bn1", x, 1, 0, fp16)), fp16)
+                out = _q(F.relu(_cb(sd, p + "conv2", p + "bn2", out, stride, 1, fp16)), fp16)
+                out = _cb(sd, p + "conv3", p + "bn3", out, 1, 0, fp16)
             else:
-                out = F.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x, stride, 1)))
-                out = _bn(sd, p + "bn2", _conv(sd, p + "conv2", out, 1, 1))
+                out = _q(F.relu(_cb(sd, p + "conv1", p + "bn1", x, stride, 1, fp16)), fp16)
+                out = _cb(sd, p + "conv2", p + "bn2", out, 1, 1, fp16)
             if (p + "downsample.0.weight") in sd:
-                identity = _bn(sd, p + "downsample.1", _conv(sd, p + "downsample.0", x, stride))
-            x = F.relu(out + identity)
+                identity = _q(_cb(sd, p + "downsample.0", p + "downsample.1", x, stride, 0, fp16), fp16)
+            x = _q(F.relu(out + identity), fp16)
         if li >= 1:
             outs.append(x)
     c3, c4, c5 = outs
     n = "backbones.%s." % backbone
-    p5 = _conv(sd, n + "lateral5", c5)
-    p4 = F.interpolate(p5, scale_factor=2) + _conv(sd, n + "lateral4", c4)
-    p3 = F.interpolate(p4, scale_factor=2) + _conv(sd, n + "lateral3", c3)
-    p6 = _conv(sd, n + "pyramid6", c5, 2, 1)
-    p7 = _conv(sd, n + "pyramid7", F.relu(p6), 2, 1)
-    return [_conv(sd, n + "smooth3", p3, 1, 1), _conv(sd, n + "smooth4", p4, 1, 1), _conv(sd, n + "smooth5", p5, 1, 1), p6, p7]
+    p5 = _q(_cb(sd, n + "lateral5", None, c5, 1, 0, fp16), fp16)
+    p4 = _q(F.interpolate(p5, scale_factor=2) + _cb(sd, n + "lateral4", None, c4, 1, 0, fp16), fp16)
+    p3 = _q(F.interpolate(p4, scale_factor=2) + _cb(sd, n + "lateral3", None, c3, 1, 0, fp16), fp16)
+    p6 = _q(_cb(sd, n + "pyramid6", None, c5, 2, 1, fp16), fp16)
+    p7 = _q(_cb(sd, n + "pyramid7", None, F.relu(p6), 2, 1, fp16), fp16)
+    return [_q(_cb(sd, n + "smooth3", None, p3, 1, 1, fp16), fp16), _q(_cb(sd, n + "smooth4", None, p4, 1, 1, fp16), fp16),
+            _q(_cb(sd, n + "smooth5", None, p5, 1, 1, fp16), fp16), p6, p7]
 
 
-def head(sd, name, t):
+def head(sd, name, t, fp16=False):
     for i in (0, 2, 4, 6):
-        t = F.relu(_conv(sd, "%s.%d" % (name, i), t, 1, 1))
-    return _conv(sd, "%s.8" % name, t, 1, 1)
+        t = _q(F.relu(_cb(sd, "%s.%d" % (name, i), None, t, 1, 1, fp16)), fp16)
+    return _cb(sd, "%s.8" % name, None, t, 1, 1, fp16)            # head outputs stay fp32
 
 
-def forward_heads(sd, backbone, x, sigmoid=True):
-    """== reference Model.forward with exporting=True (odtk/model.py:130-144)."""
+def forward_heads(sd, backbone, x, sigmoid=True, fp16=False):
+    """== reference Model.forward with exporting=True (odtk/model.py:130-144); fp16=True: with the product path's
+    roundings (see above)."""
     with torch.no_grad():
         sd = {k: v.float() for k, v in sd.items()}
-        feats = features(sd, backbone, x.float())
-        cls = [head(sd, "cls_head", t) for t in feats]
-        box = [head(sd, "box_head", t) for t in feats]
+        feats = features(sd, backbone, x.float(), fp16)
+        cls = [head(sd, "cls_head", t, fp16) for t in feats]
+        box = [head(sd, "box_head", t, fp16) for t in feats]
         if sigmoid:
             cls = [c.sigmoid() for c in cls]
     return cls, box
@@ -98,6 +125,6 @@ def postprocess(cls_heads, box_heads, width, ratios=None, scales=None, angles=No
     return oracle.nms(cat[0], cat[1], cat[2], nms, detections, rotated=rotated, return_index=return_index), cat
 
 
-def forward(sd, backbone, x, **kw):
-    cls, box = forward_heads(sd, backbone, x)
+def forward(sd, backbone, x, fp16=False, **kw):
+    cls, box = forward_heads(sd, backbone, x, fp16=fp16)
     return postprocess(cls, box, x.shape[-1], **kw)[0]

@@ -148,11 +148,14 @@ class FusedDecode:
 
 
 def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, return_index=False,
-        fixed_angle=False):
+        fixed_angle=False, packed=None, gather=None):
     """odtk._C.nms (csrc/extensions.cpp:117-158).
     scores [B, N], boxes [B, N, 4|6], classes [B, N] fp32 CUDA contiguous; returns
     [scores [B, D], boxes [B, D, 4|6], classes [B, D]] (+ int32 kept positions [B, D] when
-    return_index, an extension used by the parity tests)."""
+    return_index, an extension used by the parity tests).  The kernel writes every output slot, so the outputs are
+    allocated uninitialised (the reference zero-fills them first, extensions.cpp:128-130).
+    Extensions: `packed` [B, D, 2 + nbox] fp32 receives the (score, box..., class) rows; `gather` (a peer.PeerGather)
+    makes the kernel push those rows into every rank's gather buffer and completes the exchange (odtk_nms_gather)."""
     _check_input(scores, "scores")
     _check_input(boxes, "boxes")
     _check_input(classes, "classes")
@@ -160,18 +163,29 @@ def nms(scores, boxes, classes, nms_thresh, detections_per_im, rotated=False, re
     nbox = 6 if rotated else 4
     batch, count = scores.size(0), scores.size(1)
     dev = scores.device
-    out_scores = torch.zeros((batch, detections_per_im), dtype=torch.float32, device=dev)
-    out_boxes = torch.zeros((batch, detections_per_im, nbox), dtype=torch.float32, device=dev)
-    out_classes = torch.zeros((batch, detections_per_im), dtype=torch.float32, device=dev)
+    out_scores = torch.empty((batch, detections_per_im), dtype=torch.float32, device=dev)
+    out_boxes = torch.empty((batch, detections_per_im, nbox), dtype=torch.float32, device=dev)
+    out_classes = torch.empty((batch, detections_per_im), dtype=torch.float32, device=dev)
     out_index = torch.empty((batch, detections_per_im), dtype=torch.int32, device=dev) if return_index else None
     inputs = _lib.ptr_array([scores.data_ptr(), boxes.data_ptr(), classes.data_ptr()])
     outputs = _lib.ptr_array([out_scores.data_ptr(), out_boxes.data_ptr(), out_classes.data_ptr()])
     idx_ptr = ctypes.c_void_p(out_index.data_ptr()) if return_index else None
+    if packed is not None:
+        _check_input(packed, "packed")
+        if tuple(packed.shape) != (batch, detections_per_im, 2 + nbox):
+            raise RuntimeError("packed must be [B, D, 2 + nbox]")
+    if gather is not None and (gather.batch != batch or gather.det != detections_per_im or gather.nbox != nbox):
+        raise RuntimeError("gather buffers were sized for another batch / detections / box format")
     args = (batch, inputs, outputs, count, int(detections_per_im), float(nms_thresh), nbox, int(bool(fixed_angle)),
-            idx_ptr)
-    size = _lib.check(L.odtk_nms_ex(*args, None, 0, None), "nms (workspace query)")
+            idx_ptr, ctypes.c_void_p(packed.data_ptr()) if packed is not None else None,
+            ctypes.byref(gather.desc) if gather is not None else None)
+    size = _lib.check(L.odtk_nms_gather(*args, None, 0, None), "nms (workspace query)")
     scratch = _workspace(size, dev)
-    _lib.check(L.odtk_nms_ex(*args, ctypes.c_void_p(scratch.data_ptr()), size, _stream()), "nms")
+    _lib.check(L.odtk_nms_gather(*args, ctypes.c_void_p(scratch.data_ptr()), size, _stream()), "nms")
+    if gather is not None:
+        _lib.check(L.odtk_gather_wait(ctypes.byref(gather.desc), batch, _stream()), "gather_wait")
+        if not torch.cuda.is_current_stream_capturing():      # a captured launch runs at replay time (Model counts those)
+            gather.steps += 1
     res = [out_scores, out_boxes, out_classes]
     if return_index:
         res.append(out_index)

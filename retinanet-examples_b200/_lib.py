@@ -45,6 +45,10 @@ SIGNATURES = {
     "odtk_nms_ex": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_nms_gather": (ctypes.c_longlong, [ctypes.c_int, _c_vpp, _c_vpp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "odtk_gather_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "odtk_iou": (ctypes.c_int, [_c_vpp, _c_vpp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "odtk_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "odtk_conv_last_plan": (ctypes.c_int, [ctypes.c_void_p]),
@@ -78,6 +82,12 @@ class Level(ctypes.Structure):
     """odtk_level_t (include/odtk_b200.h)."""
     _fields_ = [("scores", ctypes.c_void_p), ("deltas", ctypes.c_void_p), ("height", ctypes.c_size_t),
                 ("width", ctypes.c_size_t), ("scale", ctypes.c_size_t), ("anchors", _c_f32p)]
+
+
+class Gather(ctypes.Structure):
+    """odtk_gather_t (include/odtk_b200.h)."""
+    _fields_ = [("packed", ctypes.c_void_p * 8), ("flags", ctypes.c_void_p * 8), ("epoch", ctypes.c_void_p),
+                ("num_peers", ctypes.c_int), ("rank", ctypes.c_int)]
 
 
 class LossLevel(ctypes.Structure):

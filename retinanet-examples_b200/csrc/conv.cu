@@ -610,6 +610,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sg = (warp - 4) >> 2;
     const int row = q * 32 + lane;      // accumulator row == pixel inside the tile
     unsigned char *slab = smem + kPipeBytes + (warp - 4) * kSlabBytes;   // 1024-aligned: TMA-store source
+    const uint32_t slab_s = smem_u32(slab);                              // shared-space address: LDS / STS, not generic LD / ST
     const int nchunks = p.BN >> 4;
     // column split: 4 segments of cpw 16-column chunks (cpw = 1, 2, 4 for BN <= 64, 128, 256);
     // a slab row holds cpw*32 bytes = lpr lanes x 16 B and one warp access covers 32/lpr rows
@@ -712,7 +713,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (has_addend) {
 #pragma unroll
             for (int k = 0; k < 8; k++)
-              if (k < lpr) *reinterpret_cast<uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)) = pre[k];
+              if (k < lpr) sts128(slab_s + (uint32_t)((k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)), pre[k]);
             __syncwarp();
             if (seg + kEpiWarps / 4 < nsegs) fetch(seg + kEpiWarps / 4, n0, pre);
             else if (p.tma_store && !CLUSTER && tile + w_step < w_total) {
@@ -746,10 +747,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; j++) f[j] += __shfl_sync(0xffffffffu, bsrc, (cc & 1) * 16 + j);
               }
-              unsigned char *srow = slab + lane * kSlabRowBytes;
+              const uint32_t srow = slab_s + (uint32_t)(lane * kSlabRowBytes);
               const int u0 = ((2 * cc) ^ (lane & 7)) << 4, u1 = u0 ^ 16;
               if (has_addend) {
-                uint4 r0 = *reinterpret_cast<uint4 *>(srow + u0), r1 = *reinterpret_cast<uint4 *>(srow + u1);
+                uint4 r0 = lds128(srow + u0), r1 = lds128(srow + u1);
                 const __half2 *x0 = reinterpret_cast<const __half2 *>(&r0), *x1 = reinterpret_cast<const __half2 *>(&r1);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -769,8 +770,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 4; j++) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
               }
-              *reinterpret_cast<uint4 *>(srow + u0) = o0;
-              *reinterpret_cast<uint4 *>(srow + u1) = o1;
+              sts128(srow + u0, o0);
+              sts128(srow + u1, o1);
             }
           }
           if (p.tma_store) {
@@ -791,7 +792,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             if (k < lpr && pix8[k] >= 0 && lane_on) {
-              uint4 val = *reinterpret_cast<const uint4 *>(slab + (k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4));
+              uint4 val = lds128(slab_s + (uint32_t)((k * rpi + sub) * kSlabRowBytes + ((lx ^ ((k * rpi + sub) & 7)) << 4)));
               *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + (long long)pix8[k] * p.ldy + colbase + lx * 8) = val;
             }
           }

@@ -23,6 +23,7 @@
 // Arithmetic: fp32, IEEE division, no FMA contraction (-fmad=false): the PyTorch path is
 // the parity target, not the reference's --use_fast_math build.
 #include <limits.h>
+#include <string.h>
 
 #include <cub/block/block_radix_sort.cuh>
 
@@ -39,11 +40,18 @@ constexpr int kMaxDet = ODTK_MAX_DETECTIONS;
 
 struct NmsParams {
   const float *scores, *boxes, *classes;  // [B,count], [B,count,NBOX], [B,count]
-  float *out_scores, *out_boxes, *out_classes;
+  float *out_scores, *out_boxes, *out_classes;   // may be NULL when only the packed form is wanted
   int32_t *out_index;  // may be NULL
   int count, detections;
   float thresh;
   int fixed_angle;
+  // packed detections [B, D, 2 + NBOX] = (score, box..., class): the local copy and -- image-wise sharded inference,
+  // odtk/infer.py:98-102 -- the same rows pushed straight into every peer GPU's gather buffer over NVLink
+  float *packed_local;                 // [B, D, 2 + NBOX] or NULL
+  float *peer_packed[ODTK_MAX_PEERS];  // peer p's gather buffer: 2 parity halves of [W * B, D, 2 + NBOX]
+  unsigned *peer_flags[ODTK_MAX_PEERS];   // peer p's arrival counters [W]: += 1 per image of this rank
+  const unsigned *epoch;               // local step counter (device): selects the parity half
+  int num_peers, rank, batch;
 };
 
 constexpr int kPosBits = 13;  // count <= 6144 < 2^13
@@ -209,26 +217,61 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   __syncthreads();
 
   // ---- 3. outputs (nms.cu:150-156): kept..., then suppressed (score 0) up to min(D, n) ----
-  float *os = p.out_scores + (long long)img * D;
-  float *ob = p.out_boxes + (long long)img * D * NBOX;
-  float *oc = p.out_classes + (long long)img * D;
+  float *os = p.out_scores ? p.out_scores + (long long)img * D : nullptr;
+  float *ob = p.out_boxes ? p.out_boxes + (long long)img * D * NBOX : nullptr;
+  float *oc = p.out_classes ? p.out_classes + (long long)img * D : nullptr;
   int32_t *oi = p.out_index ? p.out_index + (long long)img * D : nullptr;
+  constexpr int PK = 2 + NBOX;
+  float *pk = p.packed_local ? p.packed_local + (long long)img * D * PK : nullptr;
+  const long long half = (long long)p.num_peers * p.batch * D * PK;      // floats per parity half of a gather buffer
+  const long long prow = ((p.num_peers > 0 && p.epoch) ? (long long)(*p.epoch & 1u) * half : 0) + ((long long)p.rank * p.batch + img) * D * PK;
   for (int j = t; j < D; j += kThreads) {
+    float v[PK];
+    int i = -1;
     if (j < nd) {
-      int i = (j < kept) ? sm.d.kidx[j] : sm.d.tidx[j - kept];
-      os[j] = (j < kept) ? sc[i] : 0.0f;
+      i = (j < kept) ? sm.d.kidx[j] : sm.d.tidx[j - kept];
+      v[0] = (j < kept) ? sc[i] : 0.0f;
 #pragma unroll
-      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = bx[(long long)i * NBOX + q];
-      oc[j] = cl[i];
-      if (oi) oi[j] = i;
+      for (int q = 0; q < NBOX; q++) v[1 + q] = bx[(long long)i * NBOX + q];
+      v[PK - 1] = cl[i];
     } else {
-      os[j] = 0.0f;
 #pragma unroll
-      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = 0.0f;
-      oc[j] = 0.0f;
-      if (oi) oi[j] = -1;
+      for (int q = 0; q < PK; q++) v[q] = 0.0f;
+    }
+    if (os) os[j] = v[0];
+    if (ob) {
+#pragma unroll
+      for (int q = 0; q < NBOX; q++) ob[j * NBOX + q] = v[1 + q];
+    }
+    if (oc) oc[j] = v[PK - 1];
+    if (oi) oi[j] = i;
+    if (pk) {
+#pragma unroll
+      for (int q = 0; q < PK; q++) pk[j * PK + q] = v[q];
+    }
+    for (int pr = 0; pr < p.num_peers; pr++) {       // peer-mapped stores: the all-gather happens here, row by row
+      float *dst = p.peer_packed[pr] + prow + (long long)j * PK;
+#pragma unroll
+      for (int q = 0; q < PK; q++) dst[q] = v[q];
     }
   }
+  if (p.num_peers > 0) {
+    __threadfence_system();                          // every thread's peer stores are visible system-wide ...
+    __syncthreads();
+    if (t < p.num_peers) atomicAdd_system(p.peer_flags[t] + p.rank, 1u);   // ... before the arrival is counted
+  }
+}
+
+// Completes the in-kernel all-gather on the receiving side: waits until every rank has delivered all its images of the
+// current step into this GPU's gather buffer, then advances the local step counter.  One warp.
+__global__ void gather_wait_kernel(const volatile unsigned *flags, unsigned *epoch, int num_peers, int batch) {
+  const unsigned target = (*epoch + 1u) * (unsigned)batch;
+  if ((int)threadIdx.x < num_peers) {
+    while ((int)(flags[threadIdx.x] - target) < 0) __nanosleep(64);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = *epoch + 1u;
 }
 
 template <int NBOX>
@@ -263,23 +306,57 @@ extern "C" long long odtk_nms_ex(int batch, const void *const *inputs, void *con
   // Everything lives in shared memory; a token workspace keeps the two-phase convention.
   if (!workspace || !workspace_size) return ODTK_ALIGN;
   if (workspace_size < ODTK_ALIGN) return ODTK_E_WORKSPACE;
-  if (!inputs || !outputs || !inputs[0] || !inputs[1] || !inputs[2] || !outputs[0] || !outputs[1] ||
-      !outputs[2])
-    return ODTK_E_INVALID;
+  return odtk_nms_gather(batch, inputs, outputs, count, detections_per_im, nms_thresh, nbox, fixed_angle, out_index,
+                         nullptr, nullptr, workspace, workspace_size, stream);
+}
+
+extern "C" long long odtk_nms_gather(int batch, const void *const *inputs, void *const *outputs, size_t count,
+                                     int detections_per_im, float nms_thresh, int nbox, int fixed_angle,
+                                     int32_t *out_index, void *packed, const odtk_gather_t *gather, void *workspace,
+                                     size_t workspace_size, odtk_stream_t stream) {
+  if (batch <= 0 || count == 0 || detections_per_im <= 0) return ODTK_E_INVALID;
+  if (nbox != 4 && nbox != 6) return ODTK_E_INVALID;
+  if (count > (size_t)kMaxCount || detections_per_im > kMaxDet) return ODTK_E_UNSUPPORTED;
+  if (!workspace || !workspace_size) return ODTK_ALIGN;
+  if (workspace_size < ODTK_ALIGN) return ODTK_E_WORKSPACE;
+  if (!inputs || !inputs[0] || !inputs[1] || !inputs[2]) return ODTK_E_INVALID;
+  const bool have_out = outputs && outputs[0] && outputs[1] && outputs[2];
+  if (!have_out && !packed && !(gather && gather->num_peers > 0)) return ODTK_E_INVALID;
+  if (outputs && !have_out && (outputs[0] || outputs[1] || outputs[2])) return ODTK_E_INVALID;   // all three or none
   if (((uintptr_t)inputs[1]) % (nbox == 4 ? 16 : 8)) return ODTK_E_INVALID;  // vector loads of the boxes
   NmsParams p;
+  memset(&p, 0, sizeof p);
   p.scores = (const float *)inputs[0];
   p.boxes = (const float *)inputs[1];
   p.classes = (const float *)inputs[2];
-  p.out_scores = (float *)outputs[0];
-  p.out_boxes = (float *)outputs[1];
-  p.out_classes = (float *)outputs[2];
+  if (have_out) { p.out_scores = (float *)outputs[0]; p.out_boxes = (float *)outputs[1]; p.out_classes = (float *)outputs[2]; }
   p.out_index = out_index;
   p.count = (int)count;
   p.detections = detections_per_im;
   p.thresh = nms_thresh;
   p.fixed_angle = fixed_angle;
+  p.packed_local = (float *)packed;
+  p.batch = batch;
+  if (gather && gather->num_peers > 0) {
+    if (gather->num_peers > ODTK_MAX_PEERS || gather->rank < 0 || gather->rank >= gather->num_peers || !gather->epoch)
+      return ODTK_E_INVALID;
+    for (int i = 0; i < gather->num_peers; i++) {
+      if (!gather->packed[i] || !gather->flags[i]) return ODTK_E_INVALID;
+      p.peer_packed[i] = (float *)gather->packed[i];
+      p.peer_flags[i] = gather->flags[i];
+    }
+    p.num_peers = gather->num_peers;
+    p.rank = gather->rank;
+    p.epoch = gather->epoch;
+  }
   return nbox == 4 ? launch_nms<4>(p, batch, (cudaStream_t)stream) : launch_nms<6>(p, batch, (cudaStream_t)stream);
+}
+
+extern "C" int odtk_gather_wait(const odtk_gather_t *gather, int batch, odtk_stream_t stream) {
+  if (!gather || gather->num_peers <= 0 || gather->num_peers > ODTK_MAX_PEERS || batch <= 0 || !gather->epoch) return ODTK_E_INVALID;
+  if (gather->rank < 0 || gather->rank >= gather->num_peers || !gather->flags[gather->rank]) return ODTK_E_INVALID;
+  gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gather->flags[gather->rank], gather->epoch, gather->num_peers, batch);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
 
 extern "C" long long odtk_nms(int batch, const void *const *inputs, void *const *outputs, size_t count,

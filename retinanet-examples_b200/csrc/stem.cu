@@ -149,6 +149,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int si = m >> 3, sj = half * 8 + (m & 7);   // stem pixel of this thread inside the 16 x 16 tile
     const int pix = si * 16 + sj;
     const int et = (warp - 4) * 32 + lane;       // 0 .. 255
+    const uint32_t sbias_s = smem_u32(sbias);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
@@ -156,7 +157,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ph0 = kPool * (rr / p.tiles_w), pw0 = kPool * (rr % p.tiles_w);
       const int sr = 2 * ph0 - 1 + si, sc = 2 * pw0 - 1 + sj;
       const bool inside = sr >= 0 && sr < p.OH && sc >= 0 && sc < p.OW;
-      unsigned char *stg = sstage + (it & 1) * kStageTile;
+      const uint32_t stg = smem_u32(sstage) + (uint32_t)((it & 1) * kStageTile);   // shared-space address (LDS / STS)
       mbar_wait(&bars->tmem_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
@@ -169,10 +170,9 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
         if (inside) {
           float f[16];
-          const float4 *b4 = reinterpret_cast<const float4 *>(sbias + c4 * 16);
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
-            const float4 b = b4[j4];
+            const float4 b = lds128f(sbias_s + (uint32_t)((c4 * 16 + j4 * 4) * 4));
             f[4 * j4] = __uint_as_float(v[c4 & 1][4 * j4]) + b.x;
             f[4 * j4 + 1] = __uint_as_float(v[c4 & 1][4 * j4 + 1]) + b.y;
             f[4 * j4 + 2] = __uint_as_float(v[c4 & 1][4 * j4 + 2]) + b.z;
@@ -187,8 +187,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.relu) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
           }
         }
-        *reinterpret_cast<uint4 *>(stg + pix * 128 + (((2 * c4) ^ (pix & 7)) << 4)) = o0;
-        *reinterpret_cast<uint4 *>(stg + pix * 128 + (((2 * c4 + 1) ^ (pix & 7)) << 4)) = o1;
+        sts128(stg + (uint32_t)(pix * 128 + (((2 * c4) ^ (pix & 7)) << 4)), o0);
+        sts128(stg + (uint32_t)(pix * 128 + (((2 * c4 + 1) ^ (pix & 7)) << 4)), o1);
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[buf]);       // the accumulator is in registers / shared memory: hand it back
@@ -215,7 +215,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int px = (2 * pi + di) * 16 + 2 * pj + dj;
                 const int srr = 2 * ph - 1 + di, scc = 2 * pw - 1 + dj;
                 if (!p.relu && (srr < 0 || srr >= p.OH || scc < 0 || scc >= p.OW)) continue;   // without ReLU the padding is -inf
-                const uint4 u = *reinterpret_cast<const uint4 *>(stg + px * 128 + ((c ^ (px & 7)) << 4));
+                const uint4 u = lds128(stg + (uint32_t)(px * 128 + ((c ^ (px & 7)) << 4)));
                 const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
                 for (int j = 0; j < 4; j++) best[j] = __hmax2(best[j], h[j]);

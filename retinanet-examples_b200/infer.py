@@ -17,6 +17,11 @@ def unpack_detections(packed):
     return packed[..., 0].contiguous(), packed[..., 1:-1].contiguous(), packed[..., -1].contiguous()
 
 
+def split_packed(packed):
+    """[N, D, 2 + nbox] -> (scores [N, D], boxes [N, D, nbox], classes [N, D]) as views (no copies)."""
+    return packed[..., 0], packed[..., 1:-1], packed[..., -1]
+
+
 def gather_detections(scores, boxes, classes, world=None):
     """All ranks receive the detections of every rank, rank-major (== the torch.cat of the
     reference's all_gather lists, infer.py:100-102).  One collective."""

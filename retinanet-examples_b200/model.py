@@ -166,6 +166,8 @@ class Model:
         self.fused_stem = os.environ.get("ODTK_FUSED_STEM", "1") != "0"
         self._fused = {}
         self._head_streams = None
+        self.gather = None            # peer.PeerGather: image-wise sharding, detections pushed to all ranks by the NMS kernel
+        self._packed_out = {}
 
     def __repr__(self):
         return '\n'.join(['     model: {}'.format(self.name), '  backbone: {}'.format(self.backbone),
@@ -436,7 +438,27 @@ class Model:
                                                    self.threshold, self.top_n, self.rotated_bbox, features[0].device)
         sinks = fd.begin()
         _, box_heads = self._heads(features, True, sinks)
-        return tuple(_C.nms(*fd.finish(box_heads), self.nms, self.detections, self.rotated_bbox))
+        return self._nms(fd.finish(box_heads))
+
+    def _nms(self, decoded):
+        """box.nms / nms_rotated (odtk/model.py:162-165) + the packed [B, D, 2 + nbox] rows (self.last_packed) and, when a
+        PeerGather is attached, the exchange with the other ranks -- all in the one NMS launch."""
+        b = decoded[0].shape[0]
+        key = (b, self.detections, self.rotated_bbox, decoded[0].device)
+        packed = self._packed_out.get(key)
+        if packed is None:
+            packed = self._packed_out[key] = torch.empty((b, self.detections, 2 + (6 if self.rotated_bbox else 4)),
+                                                         dtype=torch.float32, device=decoded[0].device)
+        self.last_packed = packed
+        return tuple(_C.nms(*decoded, self.nms, self.detections, self.rotated_bbox, packed=packed, gather=self.gather))
+
+    def attach_gather(self, gather):
+        """Image-wise sharded inference: every forward also delivers this rank's detections to all ranks
+        (peer.PeerGather.gathered()).  Attach BEFORE the CUDA graph of a shape is captured."""
+        self.gather = gather
+        if getattr(self, "_graphs", None):
+            self._graphs = {}
+        return self
 
     # ---- training-side losses (reference odtk/model.py:167-210) ---------------------------------------------------
     def _extract_targets(self, targets, stride, size):
@@ -495,7 +517,7 @@ class Model:
             return cls_heads, box_heads
         strides, anchors = self._level_anchors([c.shape[-1] for c in cls_heads], width)
         decoded = _C.decode_levels(cls_heads, box_heads, anchors, strides, self.threshold, self.top_n, self.rotated_bbox)
-        return tuple(_C.nms(*decoded, self.nms, self.detections, self.rotated_bbox))
+        return self._nms(decoded)
 
     # ---- CUDA graph replay ---------------------------------------------------------------------
     def enable_cuda_graph(self, enabled=True):
@@ -524,6 +546,8 @@ class Model:
         if not static_input:
             static_in.copy_(x, non_blocking=True)
         graph.replay()
+        if self.gather is not None:
+            self.gather.steps += 1
         return static_out
 
     def __call__(self, x, rotated_bbox=None, static_input=False):

@@ -261,7 +261,7 @@ def test_relu_copy():
     ((2, 100, 160, 512, 1024), 1, {"stride": 2}, {"mode": 3}),                             # even stride 2: parity split
     ((32, 7, 10, 256, 256), 3, {}, {"mode": 1, "bn": 128}),                                # few tiles: narrower N tile
     ((2, 100, 160, 128, 512), 1, {"residual": True}, {"mode": 0, "res_mma": 2}),
-    ((1, 100, 160, 256, 36), 3, {"f32": True}, {"mode": 4, "cluster": 2, "bn": 48}),           # narrow head output: cta_group::2 pairs
+    ((2, 100, 160, 256, 36), 3, {"f32": True}, {"mode": 4, "cluster": 2, "bn": 48}),           # narrow head output: cta_group::2 pairs
 ])
 def test_conv_variant_selection(shape, ks, kw, expect):
     """The host code picks the kernel variant from the shape; assert which one ran AND that it is right."""

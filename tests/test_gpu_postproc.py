@@ -196,7 +196,7 @@ def test_decode_then_nms_full_pipeline_batch2():
     for lvl, stride in enumerate(synth.LEVEL_STRIDES):
         anchors = oracle.generate_anchors(stride, oracle.DEFAULT_RATIOS, oracle.DEFAULT_SCALES).reshape(-1)
         outs_g.append(_C.decode(cls[lvl].to(DEV), deltas[lvl].to(DEV), anchors.tolist(), stride, 0.05, 1000))
-        if lvl >= 1:      # the P3 oracle pass is 23 M elements: keep CPU time bounded, check levels P4..P7
+        if True:          # all five levels incl. P3 (23 M scores: ~1 s in the C oracle)
             o = oracle.decode(cls[lvl].numpy(), deltas[lvl].numpy(), anchors, stride, 0.05, 1000)
             np.testing.assert_array_equal(outs_g[-1][0].cpu().numpy(), o[0])
             np.testing.assert_allclose(outs_g[-1][1].cpu().numpy(), o[1], atol=1e-3, rtol=0)
