@@ -133,6 +133,7 @@ class FullWorkload:
         self.host_out = torch.empty((batch, self.det, 2 + self.nbox), dtype=torch.float32).pin_memory()
         self.out = None
         self.world_gather = None
+        self.peer = None
         engine.STATS["launches"] = engine.STATS["conv_flops"] = 0
         engine.STATS["trace"] = []
         self.model.parallel_heads = False         # trace in the order step_profile() launches
@@ -147,7 +148,20 @@ class FullWorkload:
         self.launches_per_step = engine.STATS["launches"] + (3 if self.model.fused_candidates else 4)
         self.flops_per_step = engine.STATS["conv_flops"]
 
+    def enable_gather(self, world):
+        """Image-wise sharding over `world` ranks.  Default: the NMS kernel itself pushes this rank's detections into every
+        rank's gather buffer over NVLink peer memory (peer.PeerGather; inside the CUDA graph, no collective launch);
+        ODTK_BENCH_GATHER=nccl keeps round 1's host-launched ncclAllGather per step."""
+        self.world_gather = world
+        if os.environ.get("ODTK_BENCH_GATHER", "peer") != "nccl":
+            from retinanet_examples_b200 import peer
+            self.peer = peer.PeerGather(self.batch, detections=self.det, nbox=self.nbox)
+            self.model.attach_gather(self.peer)
+
     def _gather(self, out):
+        if self.peer is not None:
+            from retinanet_examples_b200 import infer
+            return infer.split_packed(self.peer.gathered())      # views of the rows the kernels already delivered
         if self.world_gather:
             from retinanet_examples_b200 import infer
             return infer.gather_detections(*out, world=self.world_gather)
@@ -170,7 +184,6 @@ class FullWorkload:
         Model.forward runs, the packed detections travel device -> pinned host.  The upload of step k+1
         is issued on a copy stream while step k computes (double-buffered, like any input pipeline;
         the reference overlaps its loader the same way), every byte still moves inside the timed region."""
-        from retinanet_examples_b200 import infer
         torch = self.torch
         main = torch.cuda.current_stream()
         if not hasattr(self, "_e2e"):
@@ -198,7 +211,7 @@ class FullWorkload:
             e["hout"] = [self.host_out, torch.empty_like(self.host_out).pin_memory()]
             e["done"] = [torch.cuda.Event(), torch.cuda.Event()]
         hout = e["hout"][e["k"] & 1] if lag else self.host_out
-        hout.copy_(infer.pack_detections(s, b, c), non_blocking=True)
+        hout.copy_(self.model.last_packed, non_blocking=True)      # the NMS kernel wrote the packed rows itself
         self._gather((s, b, c))
         if lag:
             e["done"][e["k"] & 1].record(main)
@@ -208,6 +221,26 @@ class FullWorkload:
             return
         e["k"] += 1
         main.synchronize()                                  # the step's result is on the host
+
+    def latency(self, reps=10):
+        """Single-request latency of one batch, input resident, host-blocking per call (what a caller at batch 1 sees):
+        CUDA-graph replay and eager launches (the eager path re-uses cached tensor maps, csrc/conv.cu)."""
+        torch = self.torch
+        out = {}
+        for name, fn in (("graph_ms", lambda: self.model(self.dev_x, static_input=True)), ("eager_ms", lambda: self.model.forward(self.dev_x))):
+            if self.peer is not None and name == "eager_ms":
+                continue                 # all ranks must run the same number of gathering steps
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            out[name] = round(sorted(ts)[len(ts) // 2], 3)
+        return out
 
     def units_per_step(self):
         return self.batch
@@ -221,11 +254,13 @@ class FullWorkload:
                 "detections_in_last_step": n_det,
                 "l2": "activations of a step (GBs) exceed the 126 MB L2; input batch %.0f MB" % (self.h2d_bytes / 1e6)}
 
+    PROFILE = "r02_layer_table.json"
+
     def _profiled_traffic(self):
         if not (self.backbone == "ResNet50FPN" and self.batch == 32 and not self.rotated):
             return None
         try:
-            return int(json.load(open(os.path.join(ROOT, "profiles", "r01_layer_table.json")))["summary"]["conv_dram_bytes"])
+            return int(json.load(open(os.path.join(ROOT, "profiles", self.PROFILE)))["summary"]["conv_dram_bytes"])
         except (OSError, KeyError, ValueError):
             return None
 
@@ -246,12 +281,12 @@ class FullWorkload:
                           "algorithmic_bytes_per_step": int(sum(l["bytes"] for l in self.trace)),
                           "note": "sum over the step's launches of max(FLOPs/tensor peak, operand+output bytes/HBM peak): "
                                   "the bound of layer-by-layer execution; frac_of_step = ideal / measured ms_per_step"}
-        return {"kernel": "conv_gemm_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
+        return {"kernel": "conv_gemm_kernel + stem_pool_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the
-                # committed ncu capture of this workload (tools/capture_step.py -> profiles/r01_layer_table.json)
+                # committed ncu capture of this workload (tools/capture_step.py -> profiles/r02_layer_table.json)
                 "traffic": self._profiled_traffic(),
-                "traffic_note": "bytes per step (all conv launches), from profiles/r01_layer_table.json (ncu, same workload)",
+                "traffic_note": "bytes per step (all conv launches), from profiles/%s (ncu, same workload)" % self.PROFILE,
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                 "avg_launch_ms": round(ms / n, 5), "launches_timed": n,
                 "algorithmic_flops_per_step": int(self.flops_per_step),
@@ -259,36 +294,39 @@ class FullWorkload:
 
     # ---- CPU legs (oracle port of the reference's PyTorch-CPU path; rank 0 only) --------------------
     @staticmethod
-    def cpu_run(backbone, sd, nimg, reps, H=800, W=1280, rotated=False):
+    def cpu_threads():
+        """A FIXED thread count for every CPU leg: the cores this process may run on, capped at 32 (one image's
+        convolutions stop scaling there and the GPU boxes' hosts are shared)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        return max(1, min(n, 32))
+
+    @staticmethod
+    def cpu_run(backbone, sd, nimg, reps, H=800, W=1280, rotated=False, warmup=1):
+        """`reps` timed passes of the CPU oracle port over `nimg` images each (after `warmup` untimed ones).
+        Returns (list of per-pass seconds, threads used)."""
         import torch
-        import torch.nn.functional as F
         from oracle import model_ref
-        # all host threads torch can use -- unless fewer are faster on this (shared) host: pick the best
-        # of {all, 64, 32, 16} on one representative convolution so the baseline is not handicapped
-        ncpu = os.cpu_count() or 1
-        probe_x, probe_w = torch.randn(1, 256, 100, 160), torch.randn(256, 256, 3, 3)
-        best = (1e9, ncpu)
-        for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
-            torch.set_num_threads(nt)
-            F.conv2d(probe_x, probe_w, padding=1)
-            for _ in range(3):                      # best of 3: the host is shared, single samples are noisy
-                t0 = time.perf_counter()
-                F.conv2d(probe_x, probe_w, padding=1)
-                best = min(best, (time.perf_counter() - t0, nt))
-        torch.set_num_threads(best[1])
+        nt = FullWorkload.cpu_threads()
+        torch.set_num_threads(nt)
         x = torch.randn((nimg, 3, H, W), generator=torch.Generator().manual_seed(7))
-        model_ref.forward(sd, backbone, x[:1], rotated=rotated)        # warm-up
-        t0 = time.perf_counter()
-        for _ in range(reps):
+        for _ in range(max(1, warmup)):
             model_ref.forward(sd, backbone, x, rotated=rotated)
-        dt = time.perf_counter() - t0
-        return nimg * reps / dt, torch.get_num_threads()
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            model_ref.forward(sd, backbone, x, rotated=rotated)
+            times.append(time.perf_counter() - t0)
+        return times, torch.get_num_threads()
 
     def cpu_baseline(self):
-        v, cores = self.cpu_run(self.backbone, self.sd, 1, 2, rotated=self.rotated)
-        return {"value": round(v, 3), "unit": "images/sec", "cores": cores, "kind": "port",
-                "sample": "2 x 1 image 3x800x1280 fp32, oracle/model_ref.py (torch CPU convs, same weights) + "
-                          "oracle decode/nms; the reference's own PyTorch-CPU path restated"}
+        times, cores = self.cpu_run(self.backbone, self.sd, 1, 5, rotated=self.rotated, warmup=2)
+        med = sorted(times)[len(times) // 2]
+        return {"value": round(1.0 / med, 3), "unit": "images/sec", "cores": cores, "kind": "port",
+                "sample": "median of 5 x 1 image 3x800x1280 fp32 (2 warm-up), oracle/model_ref.py (torch CPU convs, same "
+                          "weights) + oracle decode/nms, %d threads; the reference's own PyTorch-CPU path restated" % cores}
 
 
 # =================================================================================================
@@ -384,6 +422,44 @@ class PostprocWorkload:
                 "sample": "%d images of the same batch, all 5 levels, oracle/odtk_oracle.c decode+nms, 1 thread" % nimg}
 
 
+# BASELINE.json `configs` (and north_star's batch 1 / 8 / 32) as presets of the flags below
+CONFIGS = {
+    "b1": {"workload": "full", "batch": 1}, "b8": {"workload": "full", "batch": 8}, "b32": {"workload": "full", "batch": 32},
+    "rn101x8": {"workload": "full", "backbone": "ResNet101FPN", "batch": 8},      # configs[3]: launch with --gpus 8 (64 images / step)
+    "rotated": {"workload": "full", "batch": 8, "rotated": True},                  # configs[4]
+    "postproc": {"workload": "postproc", "batch": 8},                              # configs[1]
+    "postproc_rotated": {"workload": "postproc", "batch": 8, "rotated": True},
+}
+
+
+def postproc_sub(device, peaks, lib, rotated=False, batch=8, steps=30):
+    """decode + NMS alone (the second half of BASELINE.json's metric, configs[1]: head outputs of 8 images, fp32 NCHW entry
+    points): microseconds per image, device-timed, plus the streaming kernel's HBM roofline."""
+    import torch
+    wl = PostprocWorkload(batch, 0, device, rotated)
+    for _ in range(3):
+        wl.step()
+    lib.odtk_prof_reset()
+    lib.odtk_prof_enable(1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.step()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.odtk_prof_enable(0)
+    ms = e0.elapsed_time(e1)
+    roof = wl.roofline(lib, peaks, steps)
+    nms_ms, nms_n = _prof_get(lib, 2)
+    sel_ms, sel_n = _prof_get(lib, 1)
+    return {"workload": wl.name, "us_per_image": round(ms * 1e3 / steps / batch, 2), "images_per_gpu": batch, "steps": steps,
+            "images_per_sec": round(batch * steps / (ms * 1e-3), 1),
+            "hbm_floor_us_per_image": round(sum(wl.level_score_bytes) / batch / (peaks["hbm"] * 1e9) * 1e6, 2),
+            "nms_us_per_launch": round(nms_ms * 1e3 / max(nms_n, 1), 2), "select_decode_us_per_step": round(sel_ms * 1e3 / steps, 2),
+            "note": "per-kernel times come from event-bracketed launches inside the same timed loop", "roofline": roof}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,7 +472,13 @@ def main():
     ap.add_argument("--rotated", action="store_true", help="BASELINE configs[4]: --rotated-bbox model / rotated decode+NMS")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-postproc", action="store_true", help="skip the decode+NMS sub-measurement of the default line")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="BASELINE.json matrix presets: " + ", ".join("%s = %s" % kv for kv in sorted(CONFIGS.items())))
     args = ap.parse_args()
+    if args.config:
+        for k, v in CONFIGS[args.config].items():
+            setattr(args, k, v)
     args.warmup = max(args.warmup, 3)
     if not args.batch:
         args.batch = 32 if args.workload == "full" else 8
@@ -424,7 +506,10 @@ def main():
     wl = FullWorkload(args.backbone, args.batch, rank, device, args.rotated) if args.workload == "full" else \
         PostprocWorkload(args.batch, rank, device, args.rotated)
     if world > 1:
-        wl.world_gather = world
+        if hasattr(wl, "enable_gather"):
+            wl.enable_gather(world)
+        else:
+            wl.world_gather = world
 
     def barrier():
         if world > 1:
@@ -502,6 +587,16 @@ def main():
         out["e2e"] = {"value": round(units * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/sec",
                       "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                       "ms_per_step": round(ms_e2e / args.steps, 4)}
+    if world > 1 and args.workload == "full":
+        out["config"]["gather"] = ("in-kernel: every rank's NMS kernel stores its packed detections into all ranks' buffers over "
+                                   "NVLink peer memory, inside the CUDA graph (odtk_nms_gather)") if wl.peer is not None else \
+            "one host-launched ncclAllGather of the packed detections per step"
+    if world == 1 and args.workload == "full":
+        with torch.no_grad():
+            out["latency"] = wl.latency()
+    if world == 1 and args.workload == "full" and not args.no_postproc:
+        with torch.no_grad():
+            out["postproc"] = postproc_sub(device, peaks, lib, rotated=args.rotated)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = wl.cpu_baseline()
     print(json.dumps(out), flush=True)
@@ -510,51 +605,54 @@ def main():
 
 
 def reference_arm(args, rank, world):
-    """The reference's CPU implementation of the path on this box's host cores.  /root/reference
-    (Python) cannot travel to the GPU box, so this is the oracle port: oracle/model_ref.py (the same
-    torch CPU convolutions nn.Conv2d runs) + oracle decode/nms, all host threads torch can use.
-    Rank 0 only; other ranks exit 0."""
+    """The reference's CPU implementation of the path on this box's host cores.  /root/reference (Python) cannot travel to
+    the GPU box, so this is the oracle port: oracle/model_ref.py (the same torch CPU convolutions nn.Conv2d runs) +
+    oracle decode/nms.  Protocol: --warmup untimed and EXACTLY --steps timed single-image passes
+    (one image of the configured workload per step: a bounded sample), a fixed thread count, the MEDIAN pass time is
+    the reported step time.  Rank 0 only; other ranks exit 0."""
     if rank != 0:
         return
     import torch
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
     if args.workload == "postproc":
         from retinanet_examples_b200 import box, synth
         wl = PostprocWorkload.__new__(PostprocWorkload)
-        nimg = 2
+        nimg = 1
         cls, deltas = synth.head_outputs(nimg, seed=0, rotated=args.rotated, anchors=27 if args.rotated else 9)
         wl.torch, wl.batch, wl.rotated = torch, nimg, args.rotated
         wl.host = list(zip(cls, deltas))
         wl.anchors = [(box.generate_anchors_rotated(s, box.DEFAULT_RATIOS, box.DEFAULT_SCALES, box.DEFAULT_ANGLES)[0] if args.rotated
                        else box.generate_anchors(s, box.DEFAULT_RATIOS, box.DEFAULT_SCALES)).reshape(-1).tolist() for s in synth.LEVEL_STRIDES]
         wl.strides, wl.top_n, wl.det = synth.LEVEL_STRIDES, 1000, 100
-        wl.cpu_once(1)
-        steps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            wl.cpu_once(nimg)
-        dt = time.perf_counter() - t0
-        v, cores, metric, dtype = nimg * steps / dt, 1, PostprocWorkload.metric, "f32"
-        name = "decode+nms only, ResNet50FPN head shapes 3x800x1280 (BASELINE configs[1])"
-        sample = "%d steps x %d images, all 5 levels, oracle decode+nms, 1 thread" % (steps, nimg)
+        for _ in range(warmup):
+            wl.cpu_once(1)
+        times = [wl.cpu_once(nimg) for _ in range(steps)]
+        cores, metric, dtype = 1, PostprocWorkload.metric, "f32"
+        name = "decode+nms only, ResNet50FPN head shapes 3x800x1280%s (BASELINE configs[%d])" % (
+            ", rotated" if args.rotated else "", 4 if args.rotated else 1)
+        what = "1 image, all 5 levels, oracle/odtk_oracle.c decode+nms, 1 thread"
     else:
         from oracle import model_ref
         from retinanet_examples_b200 import synth
         from retinanet_examples_b200.model import make_state_dict
         sd = make_state_dict(args.backbone, 80, 27 if args.rotated else 9, args.rotated, seed=0)
+        torch.set_num_threads(FullWorkload.cpu_threads())
         probe = torch.randn((1, 3, 256, 384), generator=torch.Generator().manual_seed(3))
         sd = synth.calibrate_cls_head(sd, lambda s: model_ref.forward_heads(s, args.backbone, probe, sigmoid=False)[0])
-        steps = max(1, min(args.steps, 3))
-        v, cores = FullWorkload.cpu_run(args.backbone, sd, 1, steps, rotated=args.rotated)
-        dt = steps / v
+        times, cores = FullWorkload.cpu_run(args.backbone, sd, 1, steps, rotated=args.rotated, warmup=warmup)
         metric, dtype = FullWorkload.metric, "f32"
-        name = "%s, full backbone+FPN+heads+decode+NMS, 3x800x1280 (BASELINE configs[2] workload on the CPU path)" % args.backbone
-        sample = "%d steps x 1 image 3x800x1280 fp32, oracle/model_ref.py torch-CPU convs + oracle decode/nms, %d threads" % (steps, cores)
-    v = round(v, 3)
+        name = "%s%s, full backbone+FPN+heads+decode+NMS, 3x800x1280 (BASELINE configs[%d] workload on the CPU path)" % (
+            args.backbone, " --rotated-bbox" if args.rotated else "", 4 if args.rotated else 2)
+        what = "1 image 3x800x1280 fp32, oracle/model_ref.py torch-CPU convs + oracle decode/nms, %d threads" % cores
+    med = sorted(times)[len(times) // 2]
+    v = round(1.0 / med, 3)
+    sample = "median of %d timed steps (%d warm-up) x %s" % (steps, warmup, what)
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": name, "images_per_step": 1 if args.workload == "full" else 2},
+        "steps": steps, "warmup": warmup, "ms_per_step": round(med * 1e3, 3), "mean_ms_per_step": round(sum(times) / len(times) * 1e3, 3),
+        "min_ms_per_step": round(min(times) * 1e3, 3), "max_ms_per_step": round(max(times) * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": name, "images_per_step": 1, "host_threads": cores, "host_cpus": os.cpu_count()},
         "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 

@@ -92,3 +92,18 @@ def test_layer_table_tool_reproduces_committed_profile(tmp_path):
     assert 0.5 < new["frac"] <= 1.0
     trace = json.load(open(os.path.join(prof, "r01_step_trace.json")))
     assert sum(l["flops"] for l in trace) == 15266307768320      # 477.07 GFLOP/image x 32
+
+
+def test_plugin_shaped_wrappers_compile_and_query_sizes(tmp_path):
+    """plugins/odtk_b200_plugin.h (TensorRT-plugin-shaped enqueue / getWorkspaceSize / configurePlugin over the C ABI,
+    mirroring csrc/plugins/DecodePlugin.h:141-161 and NMSPlugin.h:120-138) compiles with stub NvInfer types, links against
+    libodtk_b200.so and answers the workspace queries without a GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "retinanet-examples_b200")
+    exe = str(tmp_path / "plugin_check")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(root, "plugins"),
+                    os.path.join(root, "plugins", "plugin_check.cpp"), "-o", exe, "-L", libdir, "-lodtk_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "decode_ws=" in out and "format_ok=1" in out
