@@ -555,6 +555,26 @@ def main():
             roof["conv_share_of_step"] = round(cms / kernel_ms, 4)
             roof["kernel_ms_per_step"] = round(kernel_ms / args.steps, 4)
             roof["eager_ms_per_step"] = round(ms_prof / args.steps, 4)
+        if roof is not None and os.environ.get("ODTK_BENCH_INSTEP") and hasattr(wl, "trace"):
+            # in-step per-layer table: per-launch event times of the LAST eager step (tags: conv 3, small layers 5), joined
+            # with the engine trace of one step in launch order
+            per = {}
+            for tag, kinds in ((3, ("conv1x1", "conv3x3", "stem7x7", "stem_pool")), (5, ("pad_input", "maxpool", "lower_conv", "relu", "preprocess_u8"))):
+                tr = [t for t in wl.trace if t["kind"] in kinds]
+                buf = (ctypes.c_float * max(1, len(tr)))()
+                n = lib.odtk_prof_get_list(tag, buf, len(tr)) if tr else 0
+                if n == len(tr):
+                    for t, v in zip(tr, buf):
+                        key = "%s %dx%dx%d %s->%s%s%s%s" % (t["kind"], t["n"], t["h"], t["w"], t["cin"], t.get("cout", ""),
+                                                          " s2" if t.get("stride") == 2 else "", " +res" if t.get("residual") else "",
+                                                          " +up" if t.get("upsample") else "")
+                        g = per.setdefault(key, {"n": 0, "ms": 0.0, "flops": 0, "bytes": 0})
+                        g["n"] += 1; g["ms"] += float(v); g["flops"] += t["flops"]; g["bytes"] += t["bytes"]
+            tot = sum(g["ms"] for g in per.values())
+            rows = [dict(layer=k, n=g["n"], us=round(g["ms"] * 1e3, 1), share=round(g["ms"] / max(tot, 1e-9), 4),
+                         tflops=round(g["flops"] / max(g["ms"], 1e-9) / 1e9, 1), gbs=round(g["bytes"] / max(g["ms"], 1e-9) / 1e6, 1))
+                    for k, g in sorted(per.items(), key=lambda kv: -kv[1]["ms"])]
+            json.dump({"sum_us": round(tot * 1e3, 1), "rows": rows}, open(os.environ["ODTK_BENCH_INSTEP"], "w"), indent=1)
         if roof is not None and getattr(wl, "layerwise", None):
             wl.layerwise["frac_of_step"] = round(wl.layerwise["ideal_ms_per_step"] / (ms / args.steps), 4)
             roof["layerwise"] = wl.layerwise

@@ -316,6 +316,8 @@ int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, int hs, int 
 void odtk_prof_enable(int on);
 void odtk_prof_reset(void);
 int odtk_prof_get(int tag, double *total_ms, long long *launches);
+/* per-launch durations (ms) of `tag`, launch order, the last `cap` launches; returns how many were written */
+long long odtk_prof_get_list(int tag, float *ms, long long cap);
 
 #ifdef __cplusplus
 }

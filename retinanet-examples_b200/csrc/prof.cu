@@ -54,3 +54,20 @@ extern "C" int odtk_prof_get(int tag, double *total_ms, long long *launches) {
   *launches = n;
   return ODTK_OK;
 }
+
+// Per-launch durations (ms) of a tag in launch order (the last `cap` launches when there are more): bench.py joins the
+// conv list of one eager step with the engine trace to show where the time goes INSIDE a running step (sustained clocks),
+// which the cold, serialised ncu launch list cannot.
+extern "C" long long odtk_prof_get_list(int tag, float *ms, long long cap) {
+  if (tag < 0 || tag >= ODTK_PROF_NTAGS || !ms || cap <= 0) return ODTK_E_INVALID;
+  if (cudaDeviceSynchronize() != cudaSuccess) return ODTK_E_CUDA;
+  const long long n = (long long)g_pairs[tag].size();
+  const long long first = n > cap ? n - cap : 0;
+  long long k = 0;
+  for (long long i = first; i < n; i++) {
+    float v = 0;
+    if (cudaEventElapsedTime(&v, g_pairs[tag][i].a, g_pairs[tag][i].b) != cudaSuccess) v = -1.0f;
+    ms[k++] = v;
+  }
+  return k;
+}

@@ -201,22 +201,27 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = item & 7, pp = item >> 3, pi = pp / kPool, pj = pp - pi * kPool;
           const int ph = ph0 + pi, pw = pw0 + pj;
           if (ph < p.PH && pw < p.PW) {
-            __half2 best[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) best[j] = __float2half2_rn(0.0f);   // inputs are >= 0 after ReLU; 0 == padding
-            if (!p.relu) {
-#pragma unroll
-              for (int j = 0; j < 4; j++) best[j] = __float2half2_rn(-65504.0f);
-            }
+            // all nine 16-byte loads first (they are volatile asm: issued in program order, so keep them adjacent and
+            // let the nine latencies overlap), then the max tree
+            uint4 u[9];
 #pragma unroll
             for (int di = 0; di < 3; di++) {
 #pragma unroll
               for (int dj = 0; dj < 3; dj++) {
                 const int px = (2 * pi + di) * 16 + 2 * pj + dj;
+                u[di * 3 + dj] = lds128(stg + (uint32_t)(px * 128 + ((c ^ (px & 7)) << 4)));
+              }
+            }
+            __half2 best[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) best[j] = __float2half2_rn(p.relu ? 0.0f : -65504.0f);   // after ReLU inputs are >= 0: 0 == padding
+#pragma unroll
+            for (int di = 0; di < 3; di++) {
+#pragma unroll
+              for (int dj = 0; dj < 3; dj++) {
                 const int srr = 2 * ph - 1 + di, scc = 2 * pw - 1 + dj;
                 if (!p.relu && (srr < 0 || srr >= p.OH || scc < 0 || scc >= p.OW)) continue;   // without ReLU the padding is -inf
-                const uint4 u = lds128(stg + (uint32_t)(px * 128 + ((c ^ (px & 7)) << 4)));
-                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u[di * 3 + dj]);
 #pragma unroll
                 for (int j = 0; j < 4; j++) best[j] = __hmax2(best[j], h[j]);
               }
