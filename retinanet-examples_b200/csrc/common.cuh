@@ -69,6 +69,48 @@ __device__ __forceinline__ void odtk_bitonic_desc_u64(unsigned long long *s, int
   }
 }
 
+#define ODTK_HIST_BINS 2048
+// Histogram suffix scan by the whole CTA: highest bin b* with sum_{bin >= b*} >= top_n, and
+// that sum.  hist has ODTK_HIST_BINS entries in shared memory; requires sum(hist) >= top_n.
+// scratch: s_w[32], s_res[2].
+__device__ __forceinline__ void odtk_find_bstar(const uint32_t *shist, int top_n, int *s_w, int *s_res,
+                                           int &bstar, int &nsel) {
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+  const int per = ODTK_HIST_BINS / T;  // bins per thread, descending order
+  int own = 0;
+  for (int q = 0; q < per; q++) own += (int)shist[ODTK_HIST_BINS - 1 - (t * per + q)];
+  int incl = own;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarp ? s_w[lane] : 0, wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_w[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  incl += s_w[warp];
+  int acc = incl - own;
+  if (acc < top_n && incl >= top_n) {
+    for (int q = 0; q < per; q++) {
+      int b = ODTK_HIST_BINS - 1 - (t * per + q);
+      acc += (int)shist[b];
+      if (acc >= top_n) { s_res[0] = b; s_res[1] = acc; break; }
+    }
+  }
+  __syncthreads();
+  bstar = s_res[0];
+  nsel = s_res[1];
+}
+
 __host__ __device__ __forceinline__ int odtk_next_pow2(int x) {
   int p = 32;
   while (p < x) p <<= 1;

@@ -35,7 +35,7 @@
 
 namespace {
 
-constexpr int kHistBins = 2048;
+constexpr int kHistBins = ODTK_HIST_BINS;
 constexpr int kSortCap = ODTK_MAX_TOP_N;  // 4096 keys of 8 B = 32 KB shared
 constexpr int kMaxAnchors = 32;           // anchor tables travel as kernel parameters
 constexpr int kMaxLevels = ODTK_MAX_LEVELS;
@@ -79,8 +79,11 @@ __device__ __forceinline__ int hist_bin(uint32_t key, uint32_t key_thresh, int s
 }
 
 // ------------------------------------------------------------------------------------
-// K1: streaming filter.  grid = sum over levels of B * blk_per_img, block = 256.
+// K1: streaming filter.  grid = sum over levels of B * blk_per_img, block = 256.  V = 16-byte vectors per lane per
+// tile (4: one 2 KB tile per warp in flight behind the one being filtered; 8: 4 KB -- more bytes in flight per SM).
+template <int V>
 __global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(const __grid_constant__ DecodeParams p) {
+  constexpr int kTileV = V * 128;            // elements per warp per iteration
   __shared__ uint2 stage[kWarpsPerBlock][kStage];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int level = 0;
@@ -125,95 +128,55 @@ __global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(const __gr
     }
   };
 
-  const long long ntiles = (n + kTile - 1) / kTile;
+  const long long ntiles = (n + kTileV - 1) / kTileV;
   const long long wstride = (long long)L.blk_per_img * kWarpsPerBlock;
   long long t = (long long)blk * kWarpsPerBlock + warp;
   if (L.vec) {
-    auto load_tile = [&](long long tt, float4 (&v)[4]) {
+    auto load_tile = [&](long long tt, float4 (&v)[V]) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        long long e = tt * kTile + (long long)(j * 32 + lane) * 4;
+      for (int j = 0; j < V; j++) {
+        long long e = tt * kTileV + (long long)(j * 32 + lane) * 4;
         // out-of-range lanes get `thresh`: thresh > thresh is false, so they never pass
         v[j] = (e < n) ? odtk_ld_stream_f4(reinterpret_cast<const float4 *>(s + e))
                        : make_float4(thresh, thresh, thresh, thresh);
       }
     };
-    float4 cur[4], nxt[4];
+    float4 cur[V], nxt[V];
     if (t < ntiles) load_tile(t, cur);
     for (; t < ntiles; t += wstride) {
       const bool more = (t + wstride) < ntiles;
       if (more) load_tile(t + wstride, nxt);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        long long e = t * kTile + (long long)(j * 32 + lane) * 4;
+      for (int j = 0; j < V; j++) {
+        long long e = t * kTileV + (long long)(j * 32 + lane) * 4;
         push(cur[j].x > thresh, cur[j].x, e + 0);
         push(cur[j].y > thresh, cur[j].y, e + 1);
         push(cur[j].z > thresh, cur[j].z, e + 2);
         push(cur[j].w > thresh, cur[j].w, e + 3);
+        if ((j & 3) == 3 && nstaged >= 32) flush();      // the staging buffer holds 32 + 512 entries
       }
-      if (nstaged >= 32) flush();
       if (more) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+        for (int j = 0; j < V; j++) cur[j] = nxt[j];
       }
     }
   } else {
     for (; t < ntiles; t += wstride) {
-      const long long e0 = t * kTile;
+      const long long e0 = t * kTileV;
       float v[16];
+      for (int h = 0; h < V / 4; h++) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        long long e = e0 + j * 32 + lane;
-        v[j] = (e < n) ? odtk_ld_stream_f1(s + e) : thresh;
+        for (int j = 0; j < 16; j++) {
+          long long e = e0 + h * 512 + j * 32 + lane;
+          v[j] = (e < n) ? odtk_ld_stream_f1(s + e) : thresh;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) push(v[j] > thresh, v[j], e0 + h * 512 + j * 32 + lane);
+        if (nstaged >= 32) flush();
       }
-#pragma unroll
-      for (int j = 0; j < 16; j++) push(v[j] > thresh, v[j], e0 + j * 32 + lane);
-      if (nstaged >= 32) flush();
     }
   }
   flush();
-}
-
-// ------------------------------------------------------------------------------------
-// Histogram suffix scan by the whole CTA: highest bin b* with sum_{bin >= b*} >= top_n, and
-// that sum.  hist has kHistBins entries in shared memory; requires sum(hist) >= top_n.
-// scratch: s_w[32], s_res[2].
-__device__ __forceinline__ void find_bstar(const uint32_t *shist, int top_n, int *s_w, int *s_res,
-                                           int &bstar, int &nsel) {
-  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
-  const int per = kHistBins / T;  // bins per thread, descending order
-  int own = 0;
-  for (int q = 0; q < per; q++) own += (int)shist[kHistBins - 1 - (t * per + q)];
-  int incl = own;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int w = lane < nwarp ? s_w[lane] : 0, wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += v;
-    }
-    s_w[lane] = wi - w;  // exclusive
-  }
-  __syncthreads();
-  incl += s_w[warp];
-  int acc = incl - own;
-  if (acc < top_n && incl >= top_n) {
-    for (int q = 0; q < per; q++) {
-      int b = kHistBins - 1 - (t * per + q);
-      acc += (int)shist[b];
-      if (acc >= top_n) { s_res[0] = b; s_res[1] = acc; break; }
-    }
-  }
-  __syncthreads();
-  bstar = s_res[0];
-  nsel = s_res[1];
 }
 
 // K2: grid = (kGatherSlices, L*B), block = 256.
@@ -231,7 +194,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_top_kernel(const __grid
   for (int i = t; i < kHistBins; i += kGatherThreads) shist[i] = hist[i];
   __syncthreads();
   int bstar, nsel;
-  find_bstar(shist, p.top_n, s_w, s_res, bstar, nsel);
+  odtk_find_bstar(shist, p.top_n, s_w, s_res, bstar, nsel);
   if (nsel > kSortCap) return;  // tie bin too large: K3 runs the exact radix select
   const uint2 *cand = p.cand + L.cand_off + (long long)img * L.cap;
   unsigned long long *sel = p.sel + (long long)slot * kSortCap;
@@ -352,7 +315,7 @@ __global__ void __launch_bounds__(1024) select_decode_kernel(const __grid_consta
       for (int i = t; i < kHistBins; i += blockDim.x) shist[i] = hist[i];
       __syncthreads();
       int bstar;
-      find_bstar(shist, p.top_n, s_w, s_misc, bstar, nsel);
+      odtk_find_bstar(shist, p.top_n, s_w, s_misc, bstar, nsel);
       if (nsel > kSortCap) slow = true;
     }
     if (!slow) {
@@ -528,6 +491,8 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
     ctas_per_sm = e ? atoi(e) : 12;  // measured on B200: 4 -> 3.7, 6 -> 4.67, 12 -> 4.79 TB/s
     if (ctas_per_sm < 1) ctas_per_sm = 12;
   }
+  static int filter_vec = 0;
+  if (!filter_vec) { const char *e = getenv("ODTK_FILTER_VEC"); filter_vec = (e && atoi(e) == 4) ? 4 : 8; }
   const long long budget = (long long)odtk_sm_count() * ctas_per_sm;
   int blk = 0;
   for (int l = 0; l < num_levels; l++) {
@@ -540,7 +505,7 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
     L.width = (int)levels[l].width;
     L.scale = (int)levels[l].scale;
     L.out_offset = (int)(out_offset + (size_t)l * top_n);
-    long long ntiles = (L.n + kTile - 1) / kTile;
+    long long ntiles = (L.n + filter_vec * 128 - 1) / (filter_vec * 128);
     long long want = (budget * L.n + total_n * batch - 1) / (total_n * batch);
     long long maxb = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (want > maxb) want = maxb;
@@ -589,7 +554,8 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
   }
   if (mode == 0) {
     OdtkProfScope prof(ODTK_PROF_FILTER, stream);
-    score_filter_kernel<<<blk, kFilterThreads, 0, stream>>>(p);
+    if (filter_vec == 8) score_filter_kernel<8><<<blk, kFilterThreads, 0, stream>>>(p);
+    else                 score_filter_kernel<4><<<blk, kFilterThreads, 0, stream>>>(p);
   }
   {
     OdtkProfScope prof(ODTK_PROF_SELECT, stream);

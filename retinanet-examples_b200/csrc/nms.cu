@@ -56,6 +56,8 @@ struct NmsParams {
 
 constexpr int kPosBits = 13;  // count <= 6144 < 2^13
 constexpr int kChunk = 128;   // ranks resolved per round
+constexpr int kPrefixMin = 512;   // prefix mode: resolve at least this many top-scoring candidates first ...
+constexpr int kPrefixCap = 2048;  // ... and at most this many (bitonic sort in shared memory)
 #ifndef ODTK_NMS_RADIX_BITS
 #define ODTK_NMS_RADIX_BITS 4
 #endif
@@ -80,14 +82,21 @@ struct NmsSmem {
     typename BlockSort::TempStorage sort;
     Data d;
   };
+  struct All {
+    U u;
+    unsigned long long sel[kPrefixCap];   // prefix mode: composites of the candidates above the selection threshold
+    uint32_t hist[ODTK_HIST_BINS];        // prefix mode: histogram of the score keys' top bits
+  };
 };
 
 template <int NBOX>
 __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typename NmsSmem<NBOX>::U &sm = *reinterpret_cast<typename NmsSmem<NBOX>::U *>(smem_raw);
+  typename NmsSmem<NBOX>::All &all = *reinterpret_cast<typename NmsSmem<NBOX>::All *>(smem_raw);
+  typename NmsSmem<NBOX>::U &sm = all.u;
   __shared__ int s_kept, s_ntail;
-  __shared__ int s_n;
+  __shared__ int s_n, s_nsel;
+  __shared__ int s_w[32], s_res[2];
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int img = blockIdx.x;
@@ -96,10 +105,11 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
   const float *bx = p.boxes + (long long)img * count * NBOX;
   const float *cl = p.classes + (long long)img * count;
 
-  // ---- 1. keys + stable descending sort (nms.cu:125-137) ---------------------------------
-  // composite = (score key << 13) | ~position: unique, so the radix sort reproduces cub's
-  // stable order of the reference.  Output is striped: thread t holds ranks t + k*1024.
-  if (t == 0) s_n = 0;
+  // ---- 1. keys (nms.cu:125-137) -------------------------------------------------------------
+  // composite = (score key << 13) | ~position: unique, so ANY descending sort of the composites reproduces cub's stable
+  // descending order of the reference.
+  if (t == 0) { s_n = 0; s_nsel = 0; }
+  for (int i = t; i < ODTK_HIST_BINS; i += kThreads) all.hist[i] = 0u;
   __syncthreads();
   unsigned long long keys[kMaxRanks];
   int nvalid = 0;
@@ -110,7 +120,9 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
     if (i < count) {
       float v = sc[i];
       if (v > 0.0f) {
-        c = ((unsigned long long)odtk_float_key(v) << kPosBits) | (unsigned)((~(unsigned)i) & ((1u << kPosBits) - 1u));
+        const uint32_t key = odtk_float_key(v);
+        c = ((unsigned long long)key << kPosBits) | (unsigned)((~(unsigned)i) & ((1u << kPosBits) - 1u));
+        atomicAdd(&all.hist[(key >> 20) & (ODTK_HIST_BINS - 1)], 1u);   // positive floats: sign bit set, 11 bits below it
         nvalid++;
       }
     }
@@ -119,102 +131,159 @@ __global__ void __launch_bounds__(kThreads) nms_batched_kernel(NmsParams p) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
   if (lane == 0 && nvalid) atomicAdd(&s_n, nvalid);
-  BlockSort(sm.sort).SortDescendingBlockedToStriped(keys, 0, 32 + kPosBits);
-  __syncthreads();  // sort scratch is dead; s_n is complete
+  __syncthreads();
   const int n = s_n;
   const int nd = n < D ? n : D;
 
-  // ---- 2. greedy NMS in chunks of 128 ranks (nms_kernel, nms.cu:49-79) ---------------------
-  // Per chunk: (A) every candidate is tested against the keepers of earlier chunks, (B) the
-  // same-class / overlap relation INSIDE the chunk is evaluated for all pairs at once into a
-  // 128 x 128 bit matrix, (C) one warp resolves the chunk sequentially with bit operations only
-  // (candidate i survives iff no earlier SURVIVOR of the chunk has its bit set in row i).  All
-  // floating-point work is parallel; the serial part is ~30 cycles per candidate and stops at D
-  // keepers -- the reference's kernel runs one block-wide barrier per candidate instead.
-  int kept = 0, ntail = 0;
-  const int nchunk = (n + kChunk - 1) / kChunk;
-  if (t == 0) { s_kept = 0; s_ntail = 0; }
-  __syncthreads();
-#pragma unroll 1
-  for (int c = 0; c < nchunk && kept < D; c++) {
-    const int r0 = c * kChunk, cn = min(kChunk, n - r0);
-    // the chunk's ranks live in threads (r0 + i) % 1024, register slot (r0 + i) / 1024
-    {
-      const int i = t - (r0 % kThreads);
-      if (i >= 0 && i < cn) {
-        unsigned long long key = 0ull;
-        const int slot = r0 / kThreads;
+  // ---- 2. order.  Prefix mode: the output needs only the first D keepers, and the greedy walk never looks back, so it
+  // is enough to order the top-scoring candidates: a histogram threshold selects between kPrefixMin and kPrefixCap of
+  // them, a bitonic sort in shared memory orders those, and only if the walk exhausts them without reaching D keepers
+  // (pathological overlap) the full block radix sort of all candidates runs.  Results are identical either way.
+  int nsel = n;
+  bool prefix = false;
+  if (n > kPrefixMin) {
+    int bstar, cnt;
+    odtk_find_bstar(all.hist, kPrefixMin, s_w, s_res, bstar, cnt);
+    if (cnt <= kPrefixCap) {
+      prefix = true;
 #pragma unroll
-        for (int k = 0; k < kMaxRanks; k++)
-          if (k == slot) key = keys[k];
-        const int idx = (int)((~(unsigned)key) & ((1u << kPosBits) - 1u));
-        if (NBOX == 4) {
-          *reinterpret_cast<float4 *>(sm.d.cbox[i]) = *reinterpret_cast<const float4 *>(bx + (long long)idx * 4);
-        } else {
+      for (int k = 0; k < kMaxRanks; k++) {
+        const unsigned long long c = keys[k];
+        if (c != 0ull && (int)((uint32_t)(c >> (kPosBits + 20)) & (ODTK_HIST_BINS - 1)) >= bstar) all.sel[atomicAdd(&s_nsel, 1)] = c;
+      }
+      __syncthreads();
+      nsel = s_nsel;                     // == cnt
+      const int P = odtk_next_pow2(nsel);
+      for (int i = nsel + t; i < P; i += kThreads) all.sel[i] = 0ull;
+      __syncthreads();
+      odtk_bitonic_desc_u64(all.sel, P);
+    }
+  } else if (n > 0) {
+    prefix = true;                       // few candidates: order all of them in shared memory
 #pragma unroll
-          for (int q = 0; q < NBOX; q += 2)
-            *reinterpret_cast<float2 *>(&sm.d.cbox[i][q]) = *reinterpret_cast<const float2 *>(bx + (long long)idx * NBOX + q);
-        }
-        sm.d.ccls[i] = (int)cl[idx];  // float -> int cast as nms.cu:55-56
-        sm.d.cidx[i] = idx;
-      }
-      if (t < kChunk) {
-        sm.d.prevsup[t] = 0;
-#pragma unroll
-        for (int w = 0; w < kChunk / 32; w++) sm.d.mask[t][w] = 0u;
-      }
-    }
+    for (int k = 0; k < kMaxRanks; k++)
+      if (keys[k] != 0ull) all.sel[atomicAdd(&s_nsel, 1)] = keys[k];
     __syncthreads();
-    // (A) against keepers of earlier chunks: pairs (i, q), i < cn, q < kept
-    for (int pidx = t; pidx < cn * kept; pidx += kThreads) {
-      const int i = pidx % cn, q = pidx / cn;
-      if (sm.d.kcls[q] == sm.d.ccls[i]) {
-        float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.kbox[q])
-                               : rotated_overlap(sm.d.cbox[i], sm.d.kbox[q], p.fixed_angle);
-        if (ov > p.thresh) sm.d.prevsup[i] = 1;
-      }
-    }
-    // (B) inside the chunk: pairs (i, j) with j < i; thread -> (i, 16 consecutive j)
-    for (int pidx = t; pidx < cn * (kChunk / 16); pidx += kThreads) {
-      const int i = pidx % cn, jg = pidx / cn;
-      unsigned bits = 0u;
-      const int icls = sm.d.ccls[i];
-#pragma unroll 4
-      for (int jj = 0; jj < 16; jj++) {
-        const int j = jg * 16 + jj;
-        if (j < i && sm.d.ccls[j] == icls) {
-          float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.cbox[j])
-                                 : rotated_overlap(sm.d.cbox[i], sm.d.cbox[j], p.fixed_angle);
-          if (ov > p.thresh) bits |= 1u << jj;
-        }
-      }
-      if (bits) atomicOr(&sm.d.mask[i][jg >> 1], bits << ((jg & 1) * 16));
-    }
+    const int P = odtk_next_pow2(n);
+    for (int i = n + t; i < P; i += kThreads) all.sel[i] = 0ull;
     __syncthreads();
-    // (C) sequential resolution by one warp: lane w (< 4) owns survivor word w of the chunk
-    if (warp == 0) {
-      unsigned surv = 0u;
-      int k2 = kept, nt2 = ntail;
-      for (int i = 0; i < cn && k2 < D; i++) {
-        const unsigned hit = (lane < kChunk / 32) ? (sm.d.mask[i][lane] & surv) : 0u;
-        const bool dead = sm.d.prevsup[i] || __any_sync(0xffffffffu, hit != 0u);
-        if (!dead) {
-          if (lane == (i >> 5)) surv |= 1u << (i & 31);
-          if (lane < NBOX) sm.d.kbox[k2][lane] = sm.d.cbox[i][lane];
-          if (lane == 0) { sm.d.kcls[k2] = sm.d.ccls[i]; sm.d.kidx[k2] = sm.d.cidx[i]; }
-          k2++;
-        } else {
-          if (lane == 0 && nt2 < D) sm.d.tidx[nt2] = sm.d.cidx[i];
-          nt2++;
-        }
-      }
-      if (lane == 0) { s_kept = k2; s_ntail = nt2; }
-    }
-    __syncthreads();
-    kept = s_kept;
-    ntail = s_ntail;
+    odtk_bitonic_desc_u64(all.sel, P);
   }
-  __syncthreads();
+
+  int kept = 0, ntail = 0;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (attempt == 1) {
+      if (!prefix || kept >= D || nsel >= n) break;        // the prefix was enough (always, on real detector outputs)
+      prefix = false;
+      nsel = n;
+    }
+    if (!prefix && n > 0) {
+      __syncthreads();
+      BlockSort(sm.sort).SortDescendingBlockedToStriped(keys, 0, 32 + kPosBits);   // thread t holds ranks t + k*1024
+      __syncthreads();                   // sort scratch is dead from here on
+    }
+
+    // ---- greedy NMS in chunks of 128 ranks (nms_kernel, nms.cu:49-79) ---------------------
+    // Per chunk: (A) every candidate is tested against the keepers of earlier chunks, (B) the
+    // same-class / overlap relation INSIDE the chunk is evaluated for all pairs at once into a
+    // 128 x 128 bit matrix, (C) one warp resolves the chunk sequentially with bit operations only
+    // (candidate i survives iff no earlier SURVIVOR of the chunk has its bit set in row i).  All
+    // floating-point work is parallel; the serial part is ~30 cycles per candidate and stops at D
+    // keepers -- the reference's kernel runs one block-wide barrier per candidate instead.
+    kept = 0; ntail = 0;
+    const int nchunk = (nsel + kChunk - 1) / kChunk;
+    if (t == 0) { s_kept = 0; s_ntail = 0; }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < nchunk && kept < D; c++) {
+      const int r0 = c * kChunk, cn = min(kChunk, nsel - r0);
+      {
+        unsigned long long key = 0ull;
+        bool mine = false;
+        if (prefix) {
+          mine = t < cn;
+          if (mine) key = all.sel[r0 + t];
+        } else {
+          // the chunk's ranks live in threads (r0 + i) % 1024, register slot (r0 + i) / 1024
+          const int i = t - (r0 % kThreads);
+          mine = i >= 0 && i < cn;
+          const int slot = r0 / kThreads;
+#pragma unroll
+          for (int k = 0; k < kMaxRanks; k++)
+            if (k == slot) key = keys[k];
+        }
+        if (mine) {
+          const int i = prefix ? t : t - (r0 % kThreads);
+          const int idx = (int)((~(unsigned)key) & ((1u << kPosBits) - 1u));
+          if (NBOX == 4) {
+            *reinterpret_cast<float4 *>(sm.d.cbox[i]) = *reinterpret_cast<const float4 *>(bx + (long long)idx * 4);
+          } else {
+#pragma unroll
+            for (int q = 0; q < NBOX; q += 2)
+              *reinterpret_cast<float2 *>(&sm.d.cbox[i][q]) = *reinterpret_cast<const float2 *>(bx + (long long)idx * NBOX + q);
+          }
+          sm.d.ccls[i] = (int)cl[idx];  // float -> int cast as nms.cu:55-56
+          sm.d.cidx[i] = idx;
+        }
+        if (t < kChunk) {
+          sm.d.prevsup[t] = 0;
+#pragma unroll
+          for (int w = 0; w < kChunk / 32; w++) sm.d.mask[t][w] = 0u;
+        }
+      }
+      __syncthreads();
+      // (A) against keepers of earlier chunks: pairs (i, q), i < cn, q < kept
+      for (int pidx = t; pidx < cn * kept; pidx += kThreads) {
+        const int i = pidx % cn, q = pidx / cn;
+        if (sm.d.kcls[q] == sm.d.ccls[i]) {
+          float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.kbox[q])
+                                 : rotated_overlap(sm.d.cbox[i], sm.d.kbox[q], p.fixed_angle);
+          if (ov > p.thresh) sm.d.prevsup[i] = 1;
+        }
+      }
+      // (B) inside the chunk: pairs (i, j) with j < i; thread -> (i, 16 consecutive j)
+      for (int pidx = t; pidx < cn * (kChunk / 16); pidx += kThreads) {
+        const int i = pidx % cn, jg = pidx / cn;
+        unsigned bits = 0u;
+        const int icls = sm.d.ccls[i];
+#pragma unroll 4
+        for (int jj = 0; jj < 16; jj++) {
+          const int j = jg * 16 + jj;
+          if (j < i && sm.d.ccls[j] == icls) {
+            float ov = (NBOX == 4) ? aligned_overlap(sm.d.cbox[i], sm.d.cbox[j])
+                                   : rotated_overlap(sm.d.cbox[i], sm.d.cbox[j], p.fixed_angle);
+            if (ov > p.thresh) bits |= 1u << jj;
+          }
+        }
+        if (bits) atomicOr(&sm.d.mask[i][jg >> 1], bits << ((jg & 1) * 16));
+      }
+      __syncthreads();
+      // (C) sequential resolution by one warp: lane w (< 4) owns survivor word w of the chunk
+      if (warp == 0) {
+        unsigned surv = 0u;
+        int k2 = kept, nt2 = ntail;
+        for (int i = 0; i < cn && k2 < D; i++) {
+          const unsigned hit = (lane < kChunk / 32) ? (sm.d.mask[i][lane] & surv) : 0u;
+          const bool dead = sm.d.prevsup[i] || __any_sync(0xffffffffu, hit != 0u);
+          if (!dead) {
+            if (lane == (i >> 5)) surv |= 1u << (i & 31);
+            if (lane < NBOX) sm.d.kbox[k2][lane] = sm.d.cbox[i][lane];
+            if (lane == 0) { sm.d.kcls[k2] = sm.d.ccls[i]; sm.d.kidx[k2] = sm.d.cidx[i]; }
+            k2++;
+          } else {
+            if (lane == 0 && nt2 < D) sm.d.tidx[nt2] = sm.d.cidx[i];
+            nt2++;
+          }
+        }
+        if (lane == 0) { s_kept = k2; s_ntail = nt2; }
+      }
+      __syncthreads();
+      kept = s_kept;
+      ntail = s_ntail;
+    }
+    __syncthreads();
+  }
 
   // ---- 3. outputs (nms.cu:150-156): kept..., then suppressed (score 0) up to min(D, n) ----
   float *os = p.out_scores ? p.out_scores + (long long)img * D : nullptr;
@@ -276,7 +345,7 @@ __global__ void gather_wait_kernel(const volatile unsigned *flags, unsigned *epo
 
 template <int NBOX>
 long long launch_nms(const NmsParams &p, int batch, cudaStream_t stream) {
-  const size_t smem = sizeof(typename NmsSmem<NBOX>::U);
+  const size_t smem = sizeof(typename NmsSmem<NBOX>::All);
   // the > 48 KB dynamic shared memory opt-in is a per-device function attribute: once per (template instance, device)
   static bool configured[64] = {};
   int dev = 0;

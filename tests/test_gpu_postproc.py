@@ -154,6 +154,25 @@ def test_nms_matches_oracle(b, n, ncls, zf, cl, thr, det):
     assert (os_ > 0).any()
 
 
+@pytest.mark.parametrize("rotated", [False, True])
+def test_nms_prefix_exhausted_falls_back_to_the_full_sort(rotated):
+    """The kernel first orders only the ~512-2048 top-scoring candidates; when the greedy walk exhausts them without
+    reaching D keepers (here: thousands of near-identical same-class boxes, so almost everything is suppressed) it must
+    run the full sort and still return exactly the oracle's result -- including the suppressed tail entries."""
+    rng = np.random.default_rng(41)
+    n = 5000
+    s = rng.uniform(0.06, 1.0, size=(2, n)).astype(np.float32)
+    ctr = rng.integers(0, 3, size=(2, n, 1)) * 400.0 + rng.normal(0, 1.0, size=(2, n, 2))
+    b = np.concatenate([ctr, ctr + 100.0], 2)
+    if rotated:
+        th = rng.uniform(-0.05, 0.05, size=(2, n, 1))
+        b = np.concatenate([b, np.sin(th), np.cos(th)], 2)
+    c = np.zeros((2, n), np.float32)
+    os_, oi = _check_nms(s, b.astype(np.float32), c, 0.5, 100, rotated=rotated)
+    assert 0 < int((os_[0] > 0).sum()) < 20          # a handful of keepers, the other output slots are suppressed entries
+    assert (oi[0] >= 0).sum() == 100
+
+
 def test_nms_edge_cases():
     rng = np.random.default_rng(3)
     s, bx, c = _nms_case(rng, 2, 200, 3, 0.0, 5)
