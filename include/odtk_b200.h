@@ -205,6 +205,9 @@ typedef struct {
   const void *bias_op;  /* optional: bias packed by odtk_conv_pack_bias ([cout, 64] fp16).  When given, the
                            bias is added by ONE extra K block on the tensor core instead of in the epilogue */
   const odtk_cand_sink_t *sink; /* out_mode ODTK_OUT_CANDIDATES: where the candidates go (host struct)       */
+  int groups;           /* 0 / 1 dense; > 1: grouped 3x3 (ResNeXt, odtk/backbones/fpn.py:85-91): cin == cout, a group never
+                           straddles a 64-channel chunk, w is [cout, 9*64] with the group's weights at the columns of
+                           its input channels inside the chunk (zeros elsewhere: block-diagonal)                   */
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
 /* Introspection (tests): the kernel variant the last odtk_conv2d / odtk_stem_conv call of the calling host thread

@@ -9,7 +9,8 @@ import torch
 
 from retinanet_examples_b200.model import make_state_dict
 
-CASES = [("ResNet18FPN", 3, 11, (1, 3, 128, 256)), ("ResNet50FPN", 3, 12, (1, 3, 128, 128))]
+CASES = [("ResNet18FPN", 3, 11, (1, 3, 128, 256)), ("ResNet50FPN", 3, 12, (1, 3, 128, 128)),
+         ("ResNeXt50_32x4dFPN", 3, 13, (1, 3, 128, 128))]      # grouped 3x3 bottlenecks (torchvision groups=32)
 
 
 def reference_heads(odtk, backbone, classes, seed, x):

@@ -18,7 +18,9 @@ from . import oracle
 
 LAYERS = {"ResNet18FPN": ("basic", [2, 2, 2, 2]), "ResNet34FPN": ("basic", [3, 4, 6, 3]),
           "ResNet50FPN": ("bottleneck", [3, 4, 6, 3]), "ResNet101FPN": ("bottleneck", [3, 4, 23, 3]),
-          "ResNet152FPN": ("bottleneck", [3, 8, 36, 3])}
+          "ResNet152FPN": ("bottleneck", [3, 8, 36, 3]),
+          "ResNeXt50_32x4dFPN": ("bottleneck", [3, 4, 6, 3]), "ResNeXt101_32x8dFPN": ("bottleneck", [3, 4, 23, 3])}
+GROUPS = {"ResNeXt50_32x4dFPN": 32, "ResNeXt101_32x8dFPN": 32}     # odtk/backbones/fpn.py:85-91 (torchvision groups=32)
 
 
 def _bn(sd, p, x):
@@ -26,8 +28,8 @@ def _bn(sd, p, x):
                         training=False, eps=1e-5)
 
 
-def _conv(sd, p, x, stride=1, padding=0):
-    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+def _conv(sd, p, x, stride=1, padding=0, groups=1):
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding, groups=groups)
 
 
 # ---- fp16-emulating mode ------------------------------------------------------------------------------------------
@@ -41,17 +43,17 @@ def _q(x, fp16):
     return x.half().float() if fp16 else x
 
 
-def _cb(sd, pconv, pbn, x, stride=1, padding=0, fp16=False):
+def _cb(sd, pconv, pbn, x, stride=1, padding=0, fp16=False, groups=1):
     """conv (+ eval BatchNorm).  fp16: folded weights rounded to fp16, fp32 accumulation, fp32 shift added after."""
     if not fp16:
-        y = _conv(sd, pconv, x, stride, padding)
+        y = _conv(sd, pconv, x, stride, padding, groups)
         return _bn(sd, pbn, y) if pbn else y
     w, b = sd[pconv + ".weight"], sd.get(pconv + ".bias")
     if pbn:
         scale = sd[pbn + ".weight"] / torch.sqrt(sd[pbn + ".running_var"] + 1e-5)
         w = w * scale.view(-1, 1, 1, 1)
         b = sd[pbn + ".bias"] - sd[pbn + ".running_mean"] * scale
-    return F.conv2d(x, w.half().float(), b, stride=stride, padding=padding)
+    return F.conv2d(x, w.half().float(), b, stride=stride, padding=padding, groups=groups)
 
 
 def features(sd, backbone, x, fp16=False):
@@ -68,7 +70,7 @@ def features(sd, backbone, x, fp16=False):
             identity = x
             if block == "bottleneck":
                 out = _q(F.relu(_cb(sd, p + "conv1", p + "bn1", x, 1, 0, fp16)), fp16)
-                out = _q(F.relu(_cb(sd, p + "conv2", p + "bn2", out, stride, 1, fp16)), fp16)
+                out = _q(F.relu(_cb(sd, p + "conv2", p + "bn2", out, stride, 1, fp16, GROUPS.get(backbone, 1))), fp16)
                 out = _cb(sd, p + "conv3", p + "bn3", out, 1, 0, fp16)
             else:
                 out = _q(F.relu(_cb(sd, p + "conv1", p + "bn1", x, stride, 1, fp16)), fp16)

@@ -246,10 +246,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (elect_one()) {
               if (TWO) {
                 if (crank == 0) mbar_arrive_expect_tx(&bars->patch_full[pb], 2u * kPatchBytes);
-                tma2_load_4d(dst, &tmA, mapa_rank(smem_u32(&bars->patch_full[pb]), 0), kc * 64, c1, c2, img);
+                tma2_load_4d(dst, &tmA, mapa_rank(smem_u32(&bars->patch_full[pb]), 0), p.grouped ? n0 : kc * 64, c1, c2, img);
               } else {
                 mbar_arrive_expect_tx(&bars->patch_full[pb], (uint32_t)kPatchBytes);
-                tma_load_4d(dst, &tmA, &bars->patch_full[pb], kc * 64, c1, c2, img);
+                tma_load_4d(dst, &tmA, &bars->patch_full[pb], p.grouped ? n0 : kc * 64, c1, c2, img);   // grouped: the N tile's own 64-channel chunk
               }
             }
             if (++pb == p.npatch) { pb = 0; pphase ^= 1u; }
@@ -304,6 +304,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             unsigned char *sa = smem + stage * kStageBytes;
             unsigned char *sb = sa + kABytes;
             const int kelems = p.row_bytes >> 1;   // K elements per block: 64 (SW128) or 32 (SW64)
+            const int kch = p.grouped ? n0 : kb * 64;   // input-channel coordinate: grouped convs read their own chunk only
             if (TWO) {
               // cta_group::2: both CTAs load their own A rows and their half of the weight rows into their own
               // shared memory; every byte is counted on the LEADER's barrier, which the leader arms for the pair
@@ -311,11 +312,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
                 if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (a_bytes + b_bytes));
                 const int half = p.BN >> 1;
-                if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kb * 64, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
+                if (p.mode == 1)      tma2_load_4d(sa, &tmA, lbar, kch, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
                 else if (p.mode == 3) {
                   const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
-                  tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
-                } else                tma2_load_2d(sa, &tmA, lbar, kb * 64, m_tile * 128);
+                  tma2_load_5d(sa, &tmA, lbar, pw * p.Cin + kch, w0 + (dx < 0 ? -1 : 0), ph, h0 + (dy < 0 ? -1 : 0), img);
+                } else                tma2_load_2d(sa, &tmA, lbar, kch, m_tile * 128);
                 tma2_load_2d(sb, &tmB, lbar, (tap * p.kblocks_per_tap + kb) * kelems, n0 + crank * half);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -323,14 +324,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
-              if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kb * 64, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
+              if (p.mode == 1)      tma_load_4d(sa, &tmA, &bars->full[stage], kch, (w0 << p.s2) + dx, (h0 << p.s2) + dy, img);
               else if (p.mode == 3) {
                 // stride 2: input pixel 2*o + d = 2*(o + (d < 0 ? -1 : 0)) + parity, on the parity-split 5-D view
                 const int pw = dx < 0 ? 1 : dx, ph = dy < 0 ? 1 : dy;
-                tma_load_5d(sa, &tmA, &bars->full[stage], pw * p.Cin + kb * 64, w0 + (dx < 0 ? -1 : 0), ph,
+                tma_load_5d(sa, &tmA, &bars->full[stage], pw * p.Cin + kch, w0 + (dx < 0 ? -1 : 0), ph,
                             h0 + (dy < 0 ? -1 : 0), img);
               }
-              else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kb * 64, m_tile * 128);
+              else if (p.mode == 0) tma_load_2d(sa, &tmA, &bars->full[stage], kch, m_tile * 128);
               else                  tma_load_5d(sa, &tmA, &bars->full[stage], 0, w0, tap, h0, img);   // stem: filter row `tap`
               if (CL2) {   // each CTA fetches half of the weight rows and multicasts them to both
                 const int half = p.BN >> 1;
@@ -1110,6 +1111,14 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (d->n <= 0 || d->h <= 0 || d->width <= 0 || d->cin <= 0 || d->cout <= 0) return ODTK_E_INVALID;
   if (d->ksize != 1 && d->ksize != 3) return ODTK_E_UNSUPPORTED;
   if (d->cin % 64 != 0) return ODTK_E_UNSUPPORTED;  // 64-channel K blocks (128-byte swizzle rows)
+  const int groups = d->groups > 1 ? d->groups : 1;
+  if (groups > 1) {
+    // grouped convolution (ResNeXt conv2): output block j of 64 channels depends only on input chunk j, as long as a
+    // group never straddles a 64-channel chunk; `w` is then [cout, ksize*ksize*64], block-diagonal inside the chunk
+    if (d->cin != d->cout || d->cin % groups || 64 % (d->cin / groups) || d->residual || d->upsample || d->ksize != 3 ||
+        d->out_mode != ODTK_OUT_NHWC_F16)
+      return ODTK_E_UNSUPPORTED;
+  }
   if (d->out_mode < 0 || d->out_mode > 3) return ODTK_E_INVALID;
   if (d->out_mode == ODTK_OUT_NHWC_F16 && (d->cout % 16)) return ODTK_E_UNSUPPORTED;
   if (d->out_mode != ODTK_OUT_NHWC_F16 && (d->residual || d->upsample)) return ODTK_E_UNSUPPORTED;
@@ -1123,12 +1132,14 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   memset(&p, 0, sizeof p);
   p.N = d->n; p.H = d->h; p.W = d->width; p.Cin = d->cin; p.Cout = d->cout;
   p.kw = d->ksize; p.taps = d->ksize * d->ksize; p.pad = d->ksize / 2;
-  p.kblocks_per_tap = d->cin / 64;
+  p.kblocks_per_tap = groups > 1 ? 1 : d->cin / 64;
+  p.grouped = groups > 1;
   p.row_bytes = 128;
   p.M = (long long)d->n * d->h * d->width;
   // N tile: whole Cout when it fits 256 columns, else the largest multiple-of-16 divisor-ish tile
   int BN;
-  if (d->cout <= 256) BN = (d->cout + 15) / 16 * 16;
+  if (groups > 1) BN = 64;
+  else if (d->cout <= 256) BN = (d->cout + 15) / 16 * 16;
   else {
     int nt = (d->cout + 255) / 256;
     BN = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
@@ -1143,7 +1154,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     long long mt = (opix + 127) / 128;
     if (d->ksize == 3 && st == 1) mt = (long long)d->n * ((d->h + 15) / 16) * ((d->width + 7) / 8);   // halo tiles (upper bound)
     const int sms = odtk_sm_count();
-    while (shrink_on && d->out_mode == ODTK_OUT_NHWC_F16 && !d->upsample && !d->residual && BN > 64 && (BN % 32) == 0 &&
+    while (shrink_on && groups == 1 && d->out_mode == ODTK_OUT_NHWC_F16 && !d->upsample && !d->residual && BN > 64 && (BN % 32) == 0 &&
            d->cout % (BN / 2) == 0 && mt * ((d->cout + BN - 1) / BN) * 2 <= sms)
       BN /= 2;
   }
@@ -1175,7 +1186,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (d->upsample && BN <= 128) return ODTK_E_UNSUPPORTED;  // the upsample-add epilogue is built for 256-wide tiles
 
   CUtensorMap tmA, tmB;
-  const uint64_t K = (uint64_t)p.taps * d->cin;
+  const uint64_t K = (uint64_t)p.taps * (groups > 1 ? 64 : d->cin);
   {
     uint64_t dims[2] = {K, (uint64_t)d->cout};
     uint64_t str[1] = {K * 2};

@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
                 ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
                 ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int), ("bias_op", ctypes.c_void_p),
-                ("sink", ctypes.c_void_p)]
+                ("sink", ctypes.c_void_p), ("groups", ctypes.c_int)]
 
 
 def _stream():
@@ -60,6 +60,21 @@ def pack_weight(weight, kpad=None):
     return w.to(torch.float16).contiguous()
 
 
+def pack_weight_grouped(weight, groups):
+    """Grouped 3x3 weights [C, C/groups, kh, kw] fp32 (ResNeXt conv2) -> [C, kh*kw*64] fp16: output channel o reads only
+    the 64-channel input chunk it lives in (a group never straddles a chunk), its group's weights sit at the columns of
+    their input channels inside that chunk, zeros elsewhere (block-diagonal)."""
+    cout, cg, kh, kw = weight.shape
+    assert cout % groups == 0 and cout // groups == cg and 64 % cg == 0 and cout % 64 == 0
+    w = weight.new_zeros((cout, kh * kw, 64))
+    o = torch.arange(cout)
+    first = (o // cg) * cg % 64                        # column of the group's first input channel inside the chunk
+    cols = first[:, None] + torch.arange(cg)[None, :]  # [cout, cg]
+    src = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw, cg)
+    w.scatter_(2, cols[:, None, :].expand(cout, kh * kw, cg), src)
+    return w.reshape(cout, kh * kw * 64).to(torch.float16).contiguous()
+
+
 def pack_bias(bias):
     """fp32 bias [Cout] (CUDA) -> the [Cout, 64] fp16 operand of the kernel's bias K block."""
     out = torch.empty((bias.numel(), 64), dtype=torch.float16, device=bias.device)
@@ -69,7 +84,7 @@ def pack_bias(bias):
 
 
 def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None,
-           stride=1, bias_op=None, sink=None):
+           stride=1, bias_op=None, sink=None, groups=1):
     """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
     Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
     assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
@@ -91,12 +106,13 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     d.n, d.h, d.width, d.cin, d.cout, d.ksize = n, h, wd, cin, cout, ksize
     d.relu, d.out_mode, d.ldy, d.ldr, d.stride = int(relu), out_mode, 0, 0, int(stride)
     d.bias_op = bias_op.data_ptr() if bias_op is not None else None
+    d.groups = int(groups)
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
     STATS["launches"] += 1
     if STATS["trace"] is not None:
         px = n * oh * ow
         obytes = 0 if out_mode == OUT_CANDIDATES else px * cout * (2 if out_mode == OUT_NHWC_F16 else 4)
-        _trace("conv%dx%d" % (ksize, ksize), 2 * px * cout * ksize * ksize * cin,
+        _trace("conv%dx%d" % (ksize, ksize), 2 * px * cout * ksize * ksize * cin // groups,
                (px * cin * 2 if (ksize == 1 and stride == 2) else x.numel() * 2) + w.numel() * 2 + obytes + (px * cout * 2 if residual is not None else 0)
                + (px * cout // 2 if upsample is not None else 0),
                n=n, h=h, w=wd, cin=cin, cout=cout, stride=int(stride), residual=residual is not None,

@@ -23,7 +23,10 @@ from . import _C, box, engine
 
 RESNET_LAYERS = {"ResNet18FPN": ("basic", [2, 2, 2, 2]), "ResNet34FPN": ("basic", [3, 4, 6, 3]),
                  "ResNet50FPN": ("bottleneck", [3, 4, 6, 3]), "ResNet101FPN": ("bottleneck", [3, 4, 23, 3]),
-                 "ResNet152FPN": ("bottleneck", [3, 8, 36, 3])}
+                 "ResNet152FPN": ("bottleneck", [3, 8, 36, 3]),
+                 "ResNeXt50_32x4dFPN": ("bottleneck", [3, 4, 6, 3]), "ResNeXt101_32x8dFPN": ("bottleneck", [3, 4, 23, 3])}
+# grouped bottlenecks (odtk/backbones/fpn.py:85-91): (groups, width_per_group); conv2 has planes * width_per_group / 64 * groups channels
+RESNEXT = {"ResNeXt50_32x4dFPN": (32, 4), "ResNeXt101_32x8dFPN": (32, 8)}
 
 
 def conv_specs(backbone, classes=80, num_anchors=9, rotated=False):
@@ -39,9 +42,11 @@ def conv_specs(backbone, classes=80, num_anchors=9, rotated=False):
             stride = 2 if (b == 0 and li > 0) else 1
             p = f + "layer%d.%d." % (li + 1, b)
             if block == "bottleneck":
-                specs += [(p + "conv1", "conv", (planes, inplanes, 1, 1)), (p + "bn1", "bn", planes),
-                          (p + "conv2", "conv", (planes, planes, 3, 3)), (p + "bn2", "bn", planes),
-                          (p + "conv3", "conv", (planes * 4, planes, 1, 1)), (p + "bn3", "bn_last", planes * 4)]
+                groups, wpg = RESNEXT.get(backbone, (1, 64))
+                width = planes * wpg // 64 * groups
+                specs += [(p + "conv1", "conv", (width, inplanes, 1, 1)), (p + "bn1", "bn", width),
+                          (p + "conv2", "conv", (width, width // groups, 3, 3)), (p + "bn2", "bn", width),
+                          (p + "conv3", "conv", (planes * 4, width, 1, 1)), (p + "bn3", "bn_last", planes * 4)]
             else:
                 specs += [(p + "conv1", "conv", (planes, inplanes, 3, 3)), (p + "bn1", "bn", planes),
                           (p + "conv2", "conv", (planes, planes, 3, 3)), (p + "bn2", "bn_last", planes)]
@@ -73,7 +78,7 @@ def make_state_dict(backbone="ResNet50FPN", classes=80, num_anchors=9, rotated=F
     for name, kind, shp in conv_specs(backbone, classes, num_anchors, rotated):
         if kind.startswith("conv"):
             cout, cin, kh, kw = shp
-            std = 0.01 if name.startswith(("cls_head", "box_head")) else math.sqrt(2.0 / (cin * kh * kw))
+            std = 0.01 if name.startswith(("cls_head", "box_head")) else math.sqrt(2.0 / (cin * kh * kw))   # cin = per-group fan-in
             sd[name + ".weight"] = torch.randn(shp, generator=g) * std
             if kind != "conv":
                 sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.01
@@ -92,8 +97,17 @@ def make_state_dict(backbone="ResNet50FPN", classes=80, num_anchors=9, rotated=F
 class _Conv:
     """One packed convolution: fp16 weights in the kernel's K order, fp32 bias, geometry."""
 
-    def __init__(self, weight, bias, stride=1, device="cuda"):
+    def __init__(self, weight, bias, stride=1, device="cuda", groups=1):
         cout, cin, kh, kw = weight.shape
+        self.groups = groups
+        if groups > 1:                       # grouped 3x3 (ResNeXt): block-diagonal packing, see engine.pack_weight_grouped
+            self.cout, self.cin, self.ks, self.stride = cout, cin * groups, kh, stride
+            self.direct, self.stem, self.w_stem = stride == 1, False, None
+            self.kpad = kh * kw * 64
+            self.w = engine.pack_weight_grouped(weight, groups).to(device)
+            self.b = bias.float().contiguous().to(device) if bias is not None else None
+            self.bop = engine.pack_bias(self.b) if self.b is not None else None
+            return
         self.cout, self.cin, self.ks, self.stride = cout, cin, kh, stride
         self.direct = stride == 1 and kh in (1, 3) and cin % 64 == 0
         self.stem = (cin == 3 and kh == 7 and stride == 2 and cout % 16 == 0 and cout <= 256)
@@ -107,13 +121,13 @@ class _Conv:
     def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False,
                  sink=None):
         oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
-        engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin
+        engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin // self.groups
         if self.stem and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and residual is None and upsample is None:
             return engine.stem_conv(x, self.w_stem, self.b, self.cout, relu)
         if self.direct:
             assert not in_relu
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode,
-                                 bias_op=self.bop, sink=sink)
+                                 bias_op=self.bop, sink=sink, groups=self.groups)
         assert sink is None
         if self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and upsample is None:
             # stride-2 convolution, any size: strided TMA view (even sizes: parity split, odd sizes: element-strided
@@ -121,7 +135,7 @@ class _Conv:
             if in_relu:
                 x = engine.relu(x)
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2,
-                                 bias_op=self.bop)
+                                 bias_op=self.bop, groups=self.groups)
         low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
         return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode, bias_op=self.bop)
 
@@ -257,10 +271,10 @@ class Model:
         sd, dev = self._sd, self.device
         P = {}
 
-        def conv_bn(prefix_conv, prefix_bn, stride=1):
+        def conv_bn(prefix_conv, prefix_bn, stride=1, groups=1):
             w, b = engine.fold_bn(sd[prefix_conv + ".weight"], sd[prefix_bn + ".weight"], sd[prefix_bn + ".bias"],
                                   sd[prefix_bn + ".running_mean"], sd[prefix_bn + ".running_var"])
-            return _Conv(w, b, stride, dev)
+            return _Conv(w, b, stride, dev, groups)
 
         def conv_b(prefix, stride=1):
             return _Conv(sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride, dev)
@@ -275,7 +289,8 @@ class Model:
                 p = f + "layer%d.%d." % (li + 1, b)
                 blk = {"level": li + 2, "last": b == nblocks - 1}
                 if block == "bottleneck":
-                    blk["convs"] = [conv_bn(p + "conv1", p + "bn1"), conv_bn(p + "conv2", p + "bn2", stride),
+                    blk["convs"] = [conv_bn(p + "conv1", p + "bn1"),
+                                    conv_bn(p + "conv2", p + "bn2", stride, RESNEXT.get(self.backbone, (1, 64))[0]),
                                     conv_bn(p + "conv3", p + "bn3")]
                 else:
                     blk["convs"] = [conv_bn(p + "conv1", p + "bn1", stride), conv_bn(p + "conv2", p + "bn2")]

@@ -327,3 +327,19 @@ def test_pad_input_rows_kernel_matches_per_pixel_layout():
         ref = torch.zeros((n, h + 6, w + 8, 4), dtype=torch.float16, device=DEV)
         ref[:, 3:3 + h, 3:3 + w, :3] = x
         np.testing.assert_array_equal(xp.float().cpu().numpy(), ref.float().cpu().numpy())
+
+
+@pytest.mark.parametrize("n,h,w,c,groups,stride", [(2, 24, 32, 128, 32, 1), (1, 50, 80, 256, 32, 1), (2, 26, 40, 512, 32, 2),
+                                                  (1, 25, 39, 256, 32, 2), (1, 16, 16, 1024, 32, 1), (2, 20, 24, 256, 32 // 2, 1)])
+def test_grouped_conv3x3_resnext(n, h, w, c, groups, stride):
+    """Grouped 3x3 (ResNeXt conv2, torchvision groups=32): each 64-channel output block reads only its own input chunk
+    (block-diagonal weights), stride 1 (halo), even stride 2 (parity split) and odd stride 2 (element-strided boxes)."""
+    g = torch.Generator().manual_seed(c + groups + h)
+    x, wt, b = _rand((n, h, w, c), g), _rand((c, c // groups, 3, 3), g, 0.1), torch.randn(c, generator=g)
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight_grouped(wt.float(), groups).to(DEV), bd, c, 3, relu=True, stride=stride,
+                      bias_op=engine.pack_bias(bd), groups=groups)
+    plan = engine.last_plan()
+    assert plan["bn"] == 64 and plan["num_n_tiles"] == c // 64, plan
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=stride, padding=1, groups=groups)
+    _close16(y, F.relu(ref))
