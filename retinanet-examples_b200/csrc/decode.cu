@@ -179,6 +179,128 @@ __global__ void __launch_bounds__(kFilterThreads) score_filter_kernel(const __gr
   flush();
 }
 
+// K1, bulk-copy variant: same filter, but the scores travel HBM -> shared memory as cp.async.bulk chunks through a ring
+// of mbarrier-guarded stages (thread 0 keeps kBulkStages - 1 chunks in flight), so the bytes in flight per SM are set by
+// the ring (6 x 8 KB per CTA), not by how many registers the compiler can spare for prefetched vectors.
+constexpr int kBulkElems = 2048;                    // floats per chunk: 8 KB = 256 threads x 2 float4
+constexpr int kBulkStages = 6;
+__global__ void __launch_bounds__(kFilterThreads) score_filter_bulk_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(128) unsigned char bulk_dyn[];       // the ring: kBulkStages x 8 KB (dynamic: static + ring > 48 KB)
+  float (*ring)[kBulkElems] = reinterpret_cast<float (*)[kBulkElems]>(bulk_dyn);
+  __shared__ uint2 stage[kWarpsPerBlock][kStage];
+  __shared__ __align__(8) unsigned long long full[kBulkStages], empty[kBulkStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int level = 0;
+#pragma unroll 1
+  for (int l = 1; l < p.num_levels; l++)
+    if ((int)blockIdx.x >= p.lv[l].blk_begin) level = l;
+  const LevelDesc &L = p.lv[level];
+  const int rel = (int)blockIdx.x - L.blk_begin;
+  const int img = rel / L.blk_per_img, blk = rel - img * L.blk_per_img;
+  const int slot = level * p.batch + img;
+  const long long n = L.n;
+  const float thresh = p.thresh;
+  const float *s = L.scores + (long long)img * n;
+  uint2 *cand = p.cand + L.cand_off + (long long)img * L.cap;
+  const long long cap = L.cap;
+  uint32_t *hist = p.hist + (long long)slot * kHistBins;
+  uint2 *st = stage[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int nstaged = 0;  // warp-uniform
+
+  auto sa = [](const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkStages; i++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(&full[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(&empty[i])), "r"(kWarpsPerBlock));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto wait = [&](unsigned long long *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                   : "=r"(done) : "r"(sa(bar)), "r"(parity) : "memory");
+    } while (!done);
+  };
+  auto flush = [&]() {
+    if (nstaged > 0) {
+      __syncwarp();
+      int base = 0;
+      if (lane == 0) base = atomicAdd(p.counts + slot, nstaged);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int j = lane; j < nstaged; j += 32) {
+        uint2 c = st[j];
+        long long dst = (long long)base + j;
+        if (dst < cap) cand[dst] = c;
+        atomicAdd(hist + hist_bin(c.x, p.key_thresh, p.shift), 1u);
+      }
+      __syncwarp();
+      nstaged = 0;
+    }
+  };
+  auto push = [&](bool pass, float v, long long idx) {
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      if (pass) st[nstaged + __popc(m & lt_mask)] = make_uint2(odtk_float_key(v), (uint32_t)idx);
+      nstaged += __popc(m);
+    }
+  };
+
+  // chunks of this (level, image) owned by this block: blk, blk + blk_per_img, ...
+  const long long nchunks = (n + kBulkElems - 1) / kBulkElems;
+  const long long mine = blk < nchunks ? (nchunks - blk + L.blk_per_img - 1) / L.blk_per_img : 0;
+  auto issue = [&](long long k) {        // thread 0: start the copy of this block's k-th chunk into stage k % kBulkStages
+    const int sidx = (int)(k % kBulkStages);
+    const long long e0 = ((long long)blk + k * L.blk_per_img) * kBulkElems;
+    const long long left = n - e0;
+    const uint32_t bytes = (uint32_t)((left >= kBulkElems ? kBulkElems : (left & ~3ll)) * 4);   // whole 16-byte units only
+    if (k >= kBulkStages) wait(&empty[sidx], (uint32_t)(((k / kBulkStages) - 1) & 1));
+    if (bytes) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sa(&full[sidx])), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sa(&ring[sidx][0])), "l"(s + e0), "r"(bytes), "r"(sa(&full[sidx])) : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sa(&full[sidx])) : "memory");
+    }
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < mine && k < kBulkStages - 1; k++) issue(k);
+  for (long long k = 0; k < mine; k++) {
+    const int sidx = (int)(k % kBulkStages);
+    if (threadIdx.x == 0 && k + kBulkStages - 1 < mine) issue(k + kBulkStages - 1);
+    wait(&full[sidx], (uint32_t)((k / kBulkStages) & 1));
+    const long long e0 = ((long long)blk + k * L.blk_per_img) * kBulkElems;
+    const long long left = n - e0;
+    const long long vec_elems = left >= kBulkElems ? kBulkElems : (left & ~3ll);
+    float4 v[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int off = (j * kFilterThreads + threadIdx.x) * 4;
+      if (off < vec_elems) v[j] = *reinterpret_cast<const float4 *>(&ring[sidx][off]);
+      else {   // tail of the level (fewer than 4 floats past the bulk copy) and the lanes beyond it
+        v[j].x = (off + 0 < left) ? odtk_ld_stream_f1(s + e0 + off + 0) : thresh;
+        v[j].y = (off + 1 < left) ? odtk_ld_stream_f1(s + e0 + off + 1) : thresh;
+        v[j].z = (off + 2 < left) ? odtk_ld_stream_f1(s + e0 + off + 2) : thresh;
+        v[j].w = (off + 3 < left) ? odtk_ld_stream_f1(s + e0 + off + 3) : thresh;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sa(&empty[sidx])) : "memory");   // stage read
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const long long e = e0 + (long long)(j * kFilterThreads + threadIdx.x) * 4;
+      push(v[j].x > thresh, v[j].x, e + 0);
+      push(v[j].y > thresh, v[j].y, e + 1);
+      push(v[j].z > thresh, v[j].z, e + 2);
+      push(v[j].w > thresh, v[j].w, e + 3);
+    }
+    if (nstaged >= 32) flush();
+  }
+  flush();
+}
+
 // K2: grid = (kGatherSlices, L*B), block = 256.
 __global__ void __launch_bounds__(kGatherThreads) gather_top_kernel(const __grid_constant__ DecodeParams p) {
   __shared__ uint32_t shist[kHistBins];
@@ -492,8 +614,13 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
     if (ctas_per_sm < 1) ctas_per_sm = 12;
   }
   static int filter_vec = 0;
-  if (!filter_vec) { const char *e = getenv("ODTK_FILTER_VEC"); filter_vec = (e && atoi(e) == 4) ? 4 : 8; }
-  const long long budget = (long long)odtk_sm_count() * ctas_per_sm;
+  if (!filter_vec) { const char *e = getenv("ODTK_FILTER_VEC"); filter_vec = (e && atoi(e) == 8) ? 8 : 4; }   // measured on B200: 4 -> 4.8 TB/s, 8 -> 3.5 TB/s (100 registers: half the resident warps)
+  static int filter_bulk = -1;
+  if (filter_bulk < 0) { const char *e = getenv("ODTK_FILTER_BULK"); filter_bulk = e ? atoi(e) : 0; }
+  bool bulk_ok = filter_bulk != 0;
+  for (int l = 0; l < num_levels && mode == 0; l++)     // bulk copies need 16-byte aligned rows of every image
+    if ((((uintptr_t)levels[l].scores) & 15) || (((long long)num_anchors * num_classes * levels[l].height * levels[l].width) & 3)) bulk_ok = false;
+  const long long budget = (long long)odtk_sm_count() * (bulk_ok ? (filter_bulk > 1 ? filter_bulk : 3) : ctas_per_sm);
   int blk = 0;
   for (int l = 0; l < num_levels; l++) {
     LevelDesc &L = p.lv[l];
@@ -505,9 +632,9 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
     L.width = (int)levels[l].width;
     L.scale = (int)levels[l].scale;
     L.out_offset = (int)(out_offset + (size_t)l * top_n);
-    long long ntiles = (L.n + filter_vec * 128 - 1) / (filter_vec * 128);
+    long long ntiles = bulk_ok ? (L.n + kBulkElems - 1) / kBulkElems : (L.n + filter_vec * 128 - 1) / (filter_vec * 128);
     long long want = (budget * L.n + total_n * batch - 1) / (total_n * batch);
-    long long maxb = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long maxb = bulk_ok ? ntiles : (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (want > maxb) want = maxb;
     if (want < 1) want = 1;
     L.blk_per_img = (int)want;
@@ -554,8 +681,19 @@ static long long decode_levels_impl(int mode, odtk_cand_sink_t *sinks, int batch
   }
   if (mode == 0) {
     OdtkProfScope prof(ODTK_PROF_FILTER, stream);
-    if (filter_vec == 8) score_filter_kernel<8><<<blk, kFilterThreads, 0, stream>>>(p);
-    else                 score_filter_kernel<4><<<blk, kFilterThreads, 0, stream>>>(p);
+    if (bulk_ok) {
+      static bool configured[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const int ring_bytes = kBulkStages * kBulkElems * (int)sizeof(float);
+      if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (cudaFuncSetAttribute(score_filter_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes) != cudaSuccess) return ODTK_E_CUDA;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+      }
+      score_filter_bulk_kernel<<<blk, kFilterThreads, ring_bytes, stream>>>(p);
+    }
+    else if (filter_vec == 8) score_filter_kernel<8><<<blk, kFilterThreads, 0, stream>>>(p);
+    else                      score_filter_kernel<4><<<blk, kFilterThreads, 0, stream>>>(p);
   }
   {
     OdtkProfScope prof(ODTK_PROF_SELECT, stream);
