@@ -373,9 +373,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             unsigned char *sa = smem + stage * kStageBytes;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + 8192u);
-              tma_load_2d(sa, &tmRes, &bars->full[stage], n0 + 64 * j, m_tile * 128);
-              tma_load_2d(sa + kABytes, &tmIdent, &bars->full[stage], 0, 0);
+              if (TWO) {   // each CTA: its own 128 residual rows + its half (32 rows) of the identity; bytes counted on the leader
+                const uint32_t lbar = mapa_rank(smem_u32(&bars->full[stage]), 0);
+                if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * ((uint32_t)kABytes + 4096u));
+                tma2_load_2d(sa, &tmRes, lbar, n0 + 64 * j, m_tile * 128);
+                tma2_load_2d(sa + kABytes, &tmIdent, lbar, 0, 32 * crank);
+              } else {
+                mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)kABytes + 8192u);
+                tma_load_2d(sa, &tmRes, &bars->full[stage], n0 + 64 * j, m_tile * 128);
+                tma_load_2d(sa + kABytes, &tmIdent, &bars->full[stage], 0, 0);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -551,7 +558,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.res_pipe) {
-          const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 64
+          const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);   // N = 64
           for (int j = 0; j < (p.BN >> 6); j++) {
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
@@ -559,8 +566,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t da = make_desc_kmajor(sa, 128), db = make_desc_kmajor(sa + kABytes, 128);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; k++) tc_mma_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
-              tc_commit(&bars->empty[stage]);
+              for (int k = 0; k < 4; k++) {
+                if (TWO) tc_mma2_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+                else     tc_mma_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc64, 1u);
+              }
+              if (TWO) tc_commit2_mc(&bars->empty[stage], (uint16_t)3); else tc_commit(&bars->empty[stage]);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -1317,7 +1327,15 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   static int two_narrow = -1;
   if (two_narrow < 0) { const char *e = getenv("ODTK_CONV_TWO_NARROW"); two_narrow = e ? atoi(e) : 1; }   // cta_group::2 pairs for narrow fp32-output head layers (halved weight stream per CTA)
   const bool narrow_pair = two_narrow && cluster_on >= 2 && p.mode == 4 && p.out_mode != ODTK_OUT_NHWC_F16 && BN >= 32 && BN <= 128;
-  if (cluster_on && (BN > 128 || narrow_pair) && !d->upsample && (!d->residual || res_pair) && (cluster_1x1 || d->ksize == 3 || res_pair) &&
+  // deep 1x1 layers (few pixels, long K): a 128 x 256 tile needs 48 KB of operands per 512 tensor-core cycles -- more than
+  // the L2 -> SM fabric delivers to 148 SMs at once; as cta_group::2 pairs (256 x 256 per pair, each CTA loads half of the
+  // weight block) the same work moves a third fewer bytes.  Big-M layers are HBM-bound and stay unclustered (measured).
+  static int deep_1x1 = -1;
+  if (deep_1x1 < 0) { const char *e = getenv("ODTK_CONV_DEEP_1X1"); deep_1x1 = e ? atoi(e) : 1; }
+  const bool deep_pair = deep_1x1 && cluster_on >= 2 && p.mode == 0 && BN == 256 && d->cin >= 256 && p.M <= 160000 &&
+                         p.out_mode == ODTK_OUT_NHWC_F16 && !d->upsample;
+  if (cluster_on && (BN > 128 || narrow_pair) && !d->upsample && (!d->residual || res_pair || deep_pair) &&
+      (cluster_1x1 || d->ksize == 3 || res_pair || deep_pair) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
       ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
@@ -1331,7 +1349,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     }
     if (ok) {
       p.cluster2 = (cluster_on >= 2 && !res_pair) ? 2 : 1;   // residual pairs: cta_group::1 MMAs, multicast weights
-      if (!(res_pair && cluster_res >= 2)) p.tma_store = 0;
+      if (!(res_pair && cluster_res >= 2) && !(deep_pair && deep_1x1 >= 1)) p.tma_store = 0;
       if (p.cluster2 == 2) { p.nstages = kPipeBytes / (kABytes + BN * 64); if (p.nstages > kMaxStages) p.nstages = kMaxStages; }
     }
     else return ODTK_E_CUDA;
@@ -1340,12 +1358,12 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   CUtensorMap tmRes = tmB, tmIdent = tmB;
   static int res_pipe_on = -1;
   if (res_pipe_on < 0) { const char *e = getenv("ODTK_CONV_RES_PIPE"); res_pipe_on = e ? atoi(e) : 1; }
-  if (res_pipe_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && !p.cluster2 && (BN % 64) == 0 &&
+  if (res_pipe_on && d->residual && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && p.cluster2 != 1 && (BN % 64) == 0 &&
       d->cout % 64 == 0 && (p.ldr % 8) == 0 && (((uintptr_t)d->residual) & 15) == 0) {
     uint64_t dimsR[2] = {(uint64_t)p.ldr, (uint64_t)p.M}, strR[1] = {(uint64_t)p.ldr * 2};
     uint32_t boxR[2] = {64, 128};
     uint64_t dimsI[2] = {64, 64}, strI[1] = {128};
-    uint32_t boxI[2] = {64, 64};
+    uint32_t boxI[2] = {64, (uint32_t)(p.cluster2 == 2 ? 32 : 64)};   // cta_group::2: each CTA holds half of the identity's rows
     if (encode_map(&tmRes, d->residual, 2, dimsR, strR, boxR) && encode_map(&tmIdent, dstate->ident64, 2, dimsI, strI, boxI))
       p.res_pipe = 1;
   }

@@ -313,3 +313,49 @@ def test_against_reference_cuda_kernels(rotated):
         if same.all():
             np.testing.assert_array_equal(gb[img][:nk], rb[img][:nk])
             np.testing.assert_array_equal(gc[img][:nk], rc[img][:nk])
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_literal_drop_in_symbols_with_data(rotated):
+    """The four literally-named drop-in entry points -- odtk_decode / odtk_decode_rotate / odtk_nms / odtk_nms_rotate, the
+    argument lists of odtk::cuda::decode(_rotate) / nms(_rotate) (csrc/cuda/*.h) -- called through raw ctypes with DATA (the
+    Python mirror and the other tests go through the _ex / _levels extensions): two-phase workspace, outputs pre-zeroed
+    by the caller as the reference's pybind layer does (extensions.cpp:83-85), results equal to the oracle."""
+    from retinanet_examples_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(99 + rotated)
+    A, nbox, stride, top_n, det = (27 if rotated else 9), (6 if rotated else 4), 32, 300, 100
+    anchors = (oracle.generate_anchors_rotated_axis(stride, oracle.DEFAULT_RATIOS, oracle.DEFAULT_SCALES, oracle.DEFAULT_ANGLES)
+               if rotated else oracle.generate_anchors(stride, oracle.DEFAULT_RATIOS, oracle.DEFAULT_SCALES)).reshape(-1)
+    cls, deltas = _level_case(rng, 2, 6, 13, 20, A, -3.0, nbox)
+    if rotated:
+        th = rng.uniform(-0.7, 0.7, size=(2, A, 13, 20))
+        d = deltas.reshape(2, A, 6, 13, 20); d[:, :, 4] = np.sin(th); d[:, :, 5] = np.cos(th)
+    tc, td = _gpu(cls), _gpu(deltas)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    s = torch.zeros((2, top_n), device=DEV); b = torch.zeros((2, top_n, nbox), device=DEV); c = torch.zeros((2, top_n), device=DEV)
+    anc = (ctypes.c_float * len(anchors))(*anchors.tolist())
+    dec = L.odtk_decode_rotate if rotated else L.odtk_decode
+    args = (2, _lib.ptr_array([tc.data_ptr(), td.data_ptr()]), _lib.ptr_array([s.data_ptr(), b.data_ptr(), c.data_ptr()]),
+            13, 20, stride, A, 6, anc, len(anchors), 0.05, top_n)
+    size = dec(*args, None, 0, None)
+    assert size > 0
+    ws = torch.empty(size, dtype=torch.uint8, device=DEV)
+    assert dec(*args, ctypes.c_void_p(ws.data_ptr()), size, st) == 0
+    os_, ob, oc = oracle.decode(cls, deltas, anchors, stride, 0.05, top_n, rotated)
+    np.testing.assert_array_equal(s.cpu().numpy(), os_)
+    np.testing.assert_array_equal(c.cpu().numpy(), oc)
+    np.testing.assert_allclose(b.cpu().numpy(), ob, atol=1e-3, rtol=0)
+    assert (os_ > 0).sum() > 50
+    ns = torch.zeros((2, det), device=DEV); nb = torch.zeros((2, det, nbox), device=DEV); nc = torch.zeros((2, det), device=DEV)
+    nms = L.odtk_nms_rotate if rotated else L.odtk_nms
+    nargs = (2, _lib.ptr_array([s.data_ptr(), b.data_ptr(), c.data_ptr()]), _lib.ptr_array([ns.data_ptr(), nb.data_ptr(), nc.data_ptr()]),
+             top_n, det, 0.5)
+    nsize = nms(*nargs, None, 0, None)
+    assert nsize > 0
+    nws = torch.empty(nsize, dtype=torch.uint8, device=DEV)
+    assert nms(*nargs, ctypes.c_void_p(nws.data_ptr()), nsize, st) == 0
+    rs, rb, rc = oracle.nms(s.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy(), 0.5, det, rotated=rotated)
+    np.testing.assert_array_equal(ns.cpu().numpy(), rs)
+    np.testing.assert_array_equal(nb.cpu().numpy(), rb)
+    np.testing.assert_array_equal(nc.cpu().numpy(), rc)

@@ -10,3 +10,7 @@ for b in 0 1 2 4 6; do
   python -c "
 import json; d=json.loads(open('gpurun_out/run7_postproc_bulk$b.json').read().strip().splitlines()[-1]); print('bulk$b', d['us_per_image'], d['roofline']['achieved'])"
 done
+timeout 300 python tools/layer_bench.py --tag r7_1x1 --only conv1x1 > gpurun_out/run7_lb_1x1.log 2>&1
+ODTK_CONV_DEEP_1X1=0 timeout 300 python tools/layer_bench.py --tag r7_1x1_nodeep --only conv1x1 > gpurun_out/run7_lb_1x1_nodeep.log 2>&1
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-postproc > gpurun_out/run7_bench.json 2> gpurun_out/run7_bench.err
+tail -c 300 gpurun_out/run7_bench.json
