@@ -208,6 +208,14 @@ typedef struct {
   int groups;           /* 0 / 1 dense; > 1: grouped 3x3 (ResNeXt, odtk/backbones/fpn.py:85-91): cin == cout, a group never
                            straddles a 64-channel chunk, w is [cout, 9*64] with the group's weights at the columns of
                            its input channels inside the chunk (zeros elsewhere: block-diagonal)                   */
+  /* Views into a larger NHWC buffer (3x3 only; 0 = dense): the pyramid ATLAS holds the five FPN levels of a batch stacked
+   * vertically in ONE [n, rows, width, C] tensor (zero gap rows between levels, zero columns right of the narrower ones),
+   * so that a head layer runs as one launch over all levels instead of five.                                           */
+  int x_rows, x_width;  /* x is the top-left h x width rectangle of images that are x_rows x x_width pixels apart        */
+  int y_rows, y_row_off, y_width; /* NHWC y: pixel (i, r, c) is written at ((i * y_rows + y_row_off + r) * y_width + c)   */
+  const void *tile_tab; /* device int32 [tab_tiles][4] = (row0, col0, row_limit, col_limit) of every 8 x 16 pixel tile of one
+                           image: x and y are then whole atlases [n, h, width, C]; only pixels below the limits are written */
+  int tab_tiles;
 } odtk_conv_t;
 int odtk_conv2d(const odtk_conv_t *desc, odtk_stream_t stream);
 /* Introspection (tests): the kernel variant the last odtk_conv2d / odtk_stem_conv call of the calling host thread
@@ -244,6 +252,10 @@ int odtk_stem_pool(const void *xp, const void *w, const float *bias, void *y, in
                    int relu, odtk_stream_t stream);
 /* y = max(x, 0), fp16, n % 8 == 0, 16-byte aligned (input of FPN pyramid7: ReLU(P6), odtk/backbones/fpn.py:55). */
 int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t stream);
+/* 3-D strided copy (+ ReLU when relu != 0) of n x rows runs of row_elems fp16 (pitches in elements, everything a multiple
+ * of 8): moves a pyramid level between a dense tensor and its rectangle of the atlas (see odtk_conv_t).          */
+int odtk_copy_rows_f16(const void *x, void *y, int n, int rows, int row_elems, long long x_img_pitch,
+                       long long x_row_pitch, long long y_img_pitch, long long y_row_pitch, int relu, odtk_stream_t stream);
 /* 3x3 stride-2 pad-1 max-pool, NHWC fp16 (torchvision resnet stem).                  */
 int odtk_maxpool3x3s2(const void *x, void *y, int n, int h, int w, int c, odtk_stream_t stream);
 

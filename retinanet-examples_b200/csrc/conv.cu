@@ -232,13 +232,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         int pb = 0;
         uint32_t pphase = 0;
-        const int per_img = p.tiles_h * p.tiles_w, half = p.BN >> 1;
+        const int per_img = p.tile_tab ? p.tab_tiles : p.tiles_h * p.tiles_w, half = p.BN >> 1;
         for (int tile = w_first; tile < w_total; tile += w_step) {
           int m_tile, n_tile;
           work_tile(tile, m_tile, n_tile);
           const int n0 = n_tile * p.BN;
           const int img = m_tile / per_img, rr = m_tile - img * per_img;
-          const int h0 = (rr / p.tiles_w) * p.TH, w0 = (rr % p.tiles_w) * p.TW;
+          int h0 = (rr / p.tiles_w) * p.TH, w0 = (rr % p.tiles_w) * p.TW;
+          if (p.tile_tab) { const int4 e = __ldg(p.tile_tab + rr); h0 = e.x; w0 = e.y; }   // pyramid atlas: tiles listed per level
           const int c1 = p.tile_t ? h0 - 1 : w0 - 1, c2 = p.tile_t ? w0 - 1 : h0 - 1;
           for (int kc = 0; kc < p.kblocks_per_tap; kc++) {
             mbar_wait(&bars->patch_empty[pb], pphase ^ 1u);
@@ -632,7 +633,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nsegs = (nchunks + cpw - 1) / cpw;
     const bool nhwc = p.out_mode == ODTK_OUT_NHWC_F16;
     const bool has_addend = (p.residual != nullptr && !p.res_mma && !p.res_pipe) || (UPS && p.upsample != nullptr);
-    const int hw = p.H * p.W, per_img = p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
+    const int hw = p.H * p.W, per_img = p.tile_tab ? p.tab_tiles : p.tiles_h * p.tiles_w, patch = p.TH * p.TW;
     // tile-relative (dh, dw) of the rows this lane touches: own row, and the slab rows k*rpi + sub
     int own_dh = 0, own_dw = 0, dh8[8], dw8[8];
     if (p.mode != 0) { own_dh = row / p.TW; own_dw = row - own_dh * p.TW; }
@@ -661,12 +662,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccStride);
       // warp-uniform tile origin
-      int img0 = 0, h0 = 0, w0 = 0;
+      int img0 = 0, h0 = 0, w0 = 0, hlim = p.H, wlim = p.W;   // hlim / wlim: first row / column NOT to be written
       if (p.mode != 0) {
         img0 = m_tile / per_img;
         const int r = m_tile - img0 * per_img;
         h0 = (r / p.tiles_w) * p.TH;
         w0 = (r % p.tiles_w) * p.TW;
+        if (p.tile_tab) { const int4 e = __ldg(p.tile_tab + r); h0 = e.x; w0 = e.y; hlim = e.z; wlim = e.w; }
       }
       if (active && nhwc) {
         // pix8: pixel index (-1: outside the tensor) of slab rows sub, rpi+sub, ...
@@ -675,7 +677,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (prefetched) break;
           if (p.mode != 0) {
             const int rr = q * 32 + k * rpi + sub, h = h0 + dh8[k], w = w0 + dw8[k];
-            pix8[k] = (k < lpr && rr < patch && h < p.H && w < p.W) ? (img0 * p.H + h) * p.W + w : -1;
+            pix8[k] = (k < lpr && rr < patch && h < hlim && w < wlim) ? (img0 * p.oH + p.oR + h) * p.oW + w : -1;
           } else {
             const int m = m_tile * 128 + dw8[k];
             pix8[k] = (k < lpr && (long long)m < p.M) ? m : -1;
@@ -815,7 +817,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool valid;
         if (p.mode != 0) {
           img = img0; h = h0 + own_dh; w = w0 + own_dw;
-          valid = row < patch && h < p.H && w < p.W;
+          valid = row < patch && h < hlim && w < wlim;
         } else {
           const int m = m_tile * 128 + row;
           valid = (long long)m < p.M;
@@ -1205,9 +1207,16 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   }
   const int stride = d->stride > 1 ? d->stride : 1;
   if (stride != 1 && stride != 2) return ODTK_E_UNSUPPORTED;
+  // strided views: the input / output may be a rectangle of a larger NHWC buffer (a level of the pyramid atlas)
+  const uint64_t xH = d->x_rows > 0 ? (uint64_t)d->x_rows : (uint64_t)d->h, xW = d->x_width > 0 ? (uint64_t)d->x_width : (uint64_t)d->width;
+  const bool x_view = xH != (uint64_t)d->h || xW != (uint64_t)d->width;
+  const bool y_view = d->y_rows > 0 || d->y_width > 0 || d->y_row_off > 0;
+  if ((x_view || y_view || d->tile_tab) && (d->ksize != 3 || d->residual || d->upsample)) return ODTK_E_UNSUPPORTED;
+  if (y_view && d->out_mode != ODTK_OUT_NHWC_F16) return ODTK_E_UNSUPPORTED;
+  if (d->tile_tab && (d->tab_tiles <= 0 || stride != 1 || x_view || y_view)) return ODTK_E_INVALID;
   static int s2_strided_box = -1;
   if (s2_strided_box < 0) { const char *e = getenv("ODTK_CONV_S2_BOX"); s2_strided_box = e ? atoi(e) : 1; }   // 2: also for even sizes
-  if (stride == 2 && !d->upsample && (((d->h & 1) || (d->width & 1)) ? s2_strided_box >= 1 : s2_strided_box >= 2)) {
+  if (stride == 2 && !d->upsample && (((d->h & 1) || (d->width & 1)) ? (s2_strided_box >= 1 || x_view) : (s2_strided_box >= 2 || x_view))) {
     // stride-2 1x1 / 3x3 (pad ksize/2) on ANY size, im2col-free: one box per tap whose W and H dimensions are
     // traversed with element stride 2 (boxDim = 2 * pixels, elementStrides = 2: the TMA unit loads every second
     // pixel); the box origin 2*o + d may be -1 or reach past the edge: zero-filled == padding.
@@ -1223,7 +1232,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     p.num_m_tiles = d->n * p.tiles_h * p.tiles_w;
     const uint64_t C = (uint64_t)d->cin, W = (uint64_t)d->width, H = (uint64_t)d->h;
     uint64_t dims[4] = {C, W, H, (uint64_t)d->n};
-    uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+    uint64_t str[3] = {C * 2, xW * C * 2, xH * xW * C * 2};
     uint32_t box[4] = {64, (uint32_t)(2 * p.TW), (uint32_t)(2 * p.TH), 1};
     uint32_t es[4] = {1, 2, 2, 1};
     if (!encode_map(&tmA, d->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, es)) return ODTK_E_CUDA;
@@ -1271,29 +1280,34 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     const bool transposed = (p.out_mode == ODTK_OUT_NHWC_F16) ? eff_b > eff_a + 1e-9 : eff_b > 1.15 * eff_a;
     const double eff_halo = transposed ? eff_b : eff_a;
     // narrow N (head outputs with few channels): the per-tap A re-load of mode 1 dominates, take the halo tiles anyway
-    if (halo_on && (eff_halo >= 0.84 * eff_free || (BN <= 64 && eff_halo >= 0.6 * eff_free)) && d->h >= 8 && d->width >= 8) {
+    if (d->tile_tab || (halo_on && (eff_halo >= 0.84 * eff_free || (BN <= 64 && eff_halo >= 0.6 * eff_free)) && d->h >= 8 && d->width >= 8)) {
       p.mode = 4;
-      p.tile_t = transposed ? 1 : 0;
+      p.tile_t = (transposed || d->tile_tab) ? 1 : 0;       // atlas tile tables list 8 x 16 (transposed) tiles
+      if (d->tile_tab) { p.tile_tab = (const int4 *)d->tile_tab; p.tab_tiles = d->tab_tiles; }
       p.halo_boff = halo_boff;
-      p.TH = transposed ? 8 : 16;
-      p.TW = transposed ? 16 : 8;
+      p.TH = p.tile_t ? 8 : 16;
+      p.TW = p.tile_t ? 16 : 8;
     }
     p.tiles_h = (d->h + p.TH - 1) / p.TH;
     p.tiles_w = (d->width + p.TW - 1) / p.TW;
-    p.num_m_tiles = d->n * p.tiles_h * p.tiles_w;
+    p.num_m_tiles = d->tile_tab ? d->n * d->tab_tiles : d->n * p.tiles_h * p.tiles_w;
     const uint64_t C = (uint64_t)d->cin, W = (uint64_t)d->width, H = (uint64_t)d->h;
     if (p.mode == 4 && p.tile_t) {   // patch stored [18 columns][16-row pitch][64 ch]: H is the faster box dimension
       uint64_t dims[4] = {C, H, W, (uint64_t)d->n};
-      uint64_t str[3] = {W * C * 2, C * 2, H * W * C * 2};
+      uint64_t str[3] = {xW * C * 2, C * 2, xH * xW * C * 2};
       uint32_t box[4] = {64, 16, 18, 1};
       if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
     } else {
       uint64_t dims[4] = {C, W, H, (uint64_t)d->n};
-      uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+      uint64_t str[3] = {C * 2, xW * C * 2, xH * xW * C * 2};
       uint32_t box[4] = {64, (uint32_t)(p.mode == 4 ? 16 : p.TW), (uint32_t)(p.mode == 4 ? 18 : p.TH), 1};
       if (!encode_map(&tmA, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
     }
   }
+  p.oH = d->y_rows > 0 ? d->y_rows : p.H;
+  p.oR = d->y_row_off > 0 ? d->y_row_off : 0;
+  p.oW = d->y_width > 0 ? d->y_width : p.W;
+  if ((long long)d->n * p.oH * p.oW >= (1ll << 31) || p.oR + p.H > p.oH || p.W > p.oW) return ODTK_E_INVALID;
   // wide 1x1 outputs (the memory-bound layers): the epilogue hands its staged slabs to the TMA unit
   CUtensorMap tmC = tmB;
   static int tma_store_on = -1;

@@ -30,6 +30,9 @@ struct ConvParams {
   int b_resident;       // halo mode: all weight blocks (+ the bias block) fit next to the patches and are loaded once per CTA
   int halo_boff;        // put (start address >> 7) & 7 into the descriptor's base-offset field
   int up_mma;           // FPN upsample-add on the tensor core: D += U * P (U = constant 128 x 64 nearest-upsample selection matrix)
+  const int4 *tile_tab;   // mode 4 over a pyramid atlas: per tile of one image (h0, w0, first row / column not to write)
+  int tab_tiles;          // tiles per image in tile_tab
+  int oH, oR, oW;         // NHWC output placement: pixel (img, h, w) is written at ((img * oH + oR + h) * oW + w) * ldy
   int grouped;          // grouped conv: kblocks_per_tap == 1 and the A channel coordinate is the N tile's own chunk (n0)
   int s2;               // mode 1: input pixel = 2 * output pixel + tap offset (element-strided TMA boxes), else 0
   int stem_rows;        // mode 5: the patch is loaded as 37 rows of 192 B (3-D map) instead of 444 pieces of 16 B (4-D map)

@@ -189,6 +189,26 @@ __global__ void relu_f16_kernel(const uint4 *__restrict__ x, uint4 *__restrict__
   }
 }
 
+// 3-D strided copy (+ optional ReLU) of fp16 rows, 16 bytes per thread: moves a pyramid level between a dense
+// [n, rows, row_elems] tensor and its rectangle inside the atlas (pitches in elements).
+__global__ void copy_rows_f16_kernel(const __half *__restrict__ x, __half *__restrict__ y, int n, int rows, int row8,
+                                     long long x_img, long long x_row, long long y_img, long long y_row, int relu) {
+  const long long total = (long long)n * rows * row8;
+  const __half2 z = __float2half2_rn(0.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % row8);
+    const long long t = i / row8;
+    const int r = (int)(t % rows), im = (int)(t / rows);
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + im * x_img + r * x_row) + c);
+    if (relu) {
+      __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; j++) h[j] = __hmax2(h[j], z);
+    }
+    reinterpret_cast<uint4 *>(y + im * y_img + r * y_row)[c] = v;
+  }
+}
+
 inline int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   long long cap = (long long)odtk_sm_count() * 16;
@@ -253,5 +273,17 @@ extern "C" int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t 
   if (!x || !y || n <= 0 || (n % 8) || (((uintptr_t)x | (uintptr_t)y) & 15)) return ODTK_E_INVALID;
   OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
   relu_f16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4 *)x, (uint4 *)y, n / 8);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
+extern "C" int odtk_copy_rows_f16(const void *x, void *y, int n, int rows, int row_elems, long long x_img_pitch,
+                                  long long x_row_pitch, long long y_img_pitch, long long y_row_pitch, int relu,
+                                  odtk_stream_t stream_) {
+  if (!x || !y || n <= 0 || rows <= 0 || row_elems <= 0 || (row_elems % 8)) return ODTK_E_INVALID;
+  if ((x_img_pitch | x_row_pitch | y_img_pitch | y_row_pitch) % 8 || (((uintptr_t)x | (uintptr_t)y) & 15)) return ODTK_E_INVALID;
+  const long long total = (long long)n * rows * (row_elems / 8);
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
+  copy_rows_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (__half *)y, n, rows, row_elems / 8,
+                                                                               x_img_pitch, x_row_pitch, y_img_pitch, y_row_pitch, relu);
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -29,7 +29,9 @@ class ConvDesc(ctypes.Structure):
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("cin", ctypes.c_int),
                 ("cout", ctypes.c_int), ("ksize", ctypes.c_int), ("relu", ctypes.c_int), ("out_mode", ctypes.c_int),
                 ("ldy", ctypes.c_int), ("ldr", ctypes.c_int), ("stride", ctypes.c_int), ("bias_op", ctypes.c_void_p),
-                ("sink", ctypes.c_void_p), ("groups", ctypes.c_int)]
+                ("sink", ctypes.c_void_p), ("groups", ctypes.c_int), ("x_rows", ctypes.c_int), ("x_width", ctypes.c_int),
+                ("y_rows", ctypes.c_int), ("y_row_off", ctypes.c_int), ("y_width", ctypes.c_int), ("tile_tab", ctypes.c_void_p),
+                ("tab_tiles", ctypes.c_int)]
 
 
 def _stream():
@@ -83,11 +85,36 @@ def pack_bias(bias):
     return out
 
 
+class AtlasView:
+    """A level of the pyramid atlas: the top-left h x w rectangle at row `row_off` of an atlas tensor [N, rows, width, C]."""
+
+    def __init__(self, atlas, row_off, h, w):
+        self.atlas, self.row_off, self.h, self.w = atlas, int(row_off), int(h), int(w)
+
+    @property
+    def shape(self):
+        return (self.atlas.shape[0], self.h, self.w, self.atlas.shape[3])
+
+    @property
+    def device(self):
+        return self.atlas.device
+
+    def dense(self):
+        """A contiguous copy of the level (tests / debugging)."""
+        return self.atlas[:, self.row_off:self.row_off + self.h, :self.w, :].contiguous()
+
+    def data_ptr(self):
+        return self.atlas.data_ptr() + self.row_off * self.atlas.shape[2] * self.atlas.shape[3] * 2
+
+
 def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, out_mode=OUT_NHWC_F16, out=None,
-           stride=1, bias_op=None, sink=None, groups=1):
-    """x: NHWC fp16 [N,H,W,Cin]; w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
-    Stride 1, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]."""
-    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
+           stride=1, bias_op=None, sink=None, groups=1, tile_tab=None):
+    """x: NHWC fp16 [N,H,W,Cin] (or an AtlasView); w: packed fp16 [Cout, ksize*ksize*Cin]; bias fp32 [Cout] or None.
+    Stride 1 / 2, pad ksize//2.  Returns NHWC fp16 [N,H,W,Cout] or NCHW fp32 [N,Cout,H,W]; `out` may be an AtlasView
+    (the result lands in that rectangle).  tile_tab (device int32 [T, 4]): x and out are whole atlases, one launch
+    covers all the levels the table lists."""
+    xv = x if isinstance(x, AtlasView) else None
+    assert xv is not None or (x.is_cuda and x.dtype == torch.float16 and x.is_contiguous())
     n, h, wd, cin = x.shape
     oh, ow = ((h - 1) // 2 + 1, (wd - 1) // 2 + 1) if stride == 2 else (h, wd)
     if out_mode == OUT_CANDIDATES:
@@ -99,6 +126,13 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
             out = torch.empty((n, cout, oh, ow), dtype=torch.float32, device=x.device)
     d = ConvDesc()
     d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), (out.data_ptr() if out is not None else None)
+    if xv is not None:
+        d.x_rows, d.x_width = xv.atlas.shape[1], xv.atlas.shape[2]
+    if isinstance(out, AtlasView):
+        d.y_rows, d.y_row_off, d.y_width = out.atlas.shape[1], 0, out.atlas.shape[2]      # data_ptr() already points at the level
+        d.y_row_off = 0
+    if tile_tab is not None:
+        d.tile_tab, d.tab_tiles = tile_tab.data_ptr(), tile_tab.shape[0]
     d.sink = ctypes.addressof(sink) if sink is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
@@ -110,10 +144,10 @@ def conv2d(x, w, bias, cout, ksize, relu=False, residual=None, upsample=None, ou
     _lib.check(_lib.lib().odtk_conv2d(ctypes.byref(d), _stream()), "conv2d")
     STATS["launches"] += 1
     if STATS["trace"] is not None:
-        px = n * oh * ow
+        px = n * oh * ow if tile_tab is None else n * int(((tile_tab[:, 2] - tile_tab[:, 0]).clamp(max=8) * (tile_tab[:, 3] - tile_tab[:, 1]).clamp(max=16)).sum())
         obytes = 0 if out_mode == OUT_CANDIDATES else px * cout * (2 if out_mode == OUT_NHWC_F16 else 4)
         _trace("conv%dx%d" % (ksize, ksize), 2 * px * cout * ksize * ksize * cin // groups,
-               (px * cin * 2 if (ksize == 1 and stride == 2) else x.numel() * 2) + w.numel() * 2 + obytes + (px * cout * 2 if residual is not None else 0)
+               (px * cin * 2 if ((ksize == 1 and stride == 2) or tile_tab is not None) else n * h * wd * cin * 2) + w.numel() * 2 + obytes + (px * cout * 2 if residual is not None else 0)
                + (px * cout // 2 if upsample is not None else 0),
                n=n, h=h, w=wd, cin=cin, cout=cout, stride=int(stride), residual=residual is not None,
                upsample=upsample is not None, out_mode=out_mode)
@@ -140,6 +174,18 @@ def relu(x):
                "relu_f16")
     STATS["launches"] += 1
     _trace("relu", 0, x.numel() * 4, n=x.shape[0], h=x.shape[1], w=x.shape[2], cin=x.shape[3])
+    return out
+
+
+def relu_from_view(view):
+    """ReLU of a pyramid level that lives inside the atlas, into a new dense tensor [N, h, w, C]."""
+    n, h, w, c = view.shape
+    a = view.atlas
+    out = torch.empty((n, h, w, c), dtype=torch.float16, device=a.device)
+    _lib.check(_lib.lib().odtk_copy_rows_f16(ctypes.c_void_p(view.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, h, w * c,
+                                             a.shape[1] * a.shape[2] * c, a.shape[2] * c, h * w * c, w * c, 1, _stream()), "copy_rows_f16")
+    STATS["launches"] += 1
+    _trace("relu", 0, out.numel() * 4, n=n, h=h, w=w, cin=c)
     return out
 
 

@@ -119,23 +119,24 @@ class _Conv:
         self.bop = engine.pack_bias(self.b) if self.b is not None else None     # bias as a tensor-core K block
 
     def __call__(self, x, relu=False, residual=None, upsample=None, out_mode=engine.OUT_NHWC_F16, in_relu=False,
-                 sink=None):
+                 sink=None, out=None, tile_tab=None, valid_px=None):
         oh, ow = (x.shape[1] - 1) // self.stride + 1, (x.shape[2] - 1) // self.stride + 1
-        engine.STATS["conv_flops"] += 2 * x.shape[0] * oh * ow * self.cout * self.ks * self.ks * self.cin // self.groups
+        px = x.shape[0] * oh * ow if valid_px is None else valid_px          # atlas launches: only the pixels of the levels count
+        engine.STATS["conv_flops"] += 2 * px * self.cout * self.ks * self.ks * self.cin // self.groups
         if self.stem and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and residual is None and upsample is None:
             return engine.stem_conv(x, self.w_stem, self.b, self.cout, relu)
         if self.direct:
             assert not in_relu
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, upsample, out_mode,
-                                 bias_op=self.bop, sink=sink, groups=self.groups)
+                                 bias_op=self.bop, sink=sink, groups=self.groups, out=out, tile_tab=tile_tab)
         assert sink is None
         if self.stride == 2 and self.ks in (1, 3) and self.cin % 64 == 0 and upsample is None:
             # stride-2 convolution, any size: strided TMA view (even sizes: parity split, odd sizes: element-strided
             # boxes), no gather pre-pass; ReLU on the input (FPN pyramid7) is one tiny elementwise launch
             if in_relu:
-                x = engine.relu(x)
+                x = engine.relu_from_view(x) if isinstance(x, engine.AtlasView) else engine.relu(x)
             return engine.conv2d(x, self.w, self.b, self.cout, self.ks, relu, residual, None, out_mode, stride=2,
-                                 bias_op=self.bop, groups=self.groups)
+                                 bias_op=self.bop, groups=self.groups, out=out)
         low = engine.lower_conv(x, self.ks, self.stride, self.ks // 2, self.kpad if self.cin % 8 else None, in_relu)
         return engine.conv2d(low, self.w, self.b, self.cout, 1, relu, residual, upsample, out_mode, bias_op=self.bop)
 
@@ -178,6 +179,8 @@ class Model:
         self.parallel_heads = True
         self.fused_candidates = os.environ.get("ODTK_FUSED_CANDIDATES", "1") != "0"
         self.fused_stem = os.environ.get("ODTK_FUSED_STEM", "1") != "0"
+        self.merged_heads = os.environ.get("ODTK_MERGED_HEADS", "1") != "0"
+        self._atlas = {}
         self._fused = {}
         self._head_streams = None
         self.gather = None            # peer.PeerGather: image-wise sharding, detections pushed to all ranks by the NMS kernel
@@ -345,9 +348,46 @@ class Model:
         p5 = P["lateral5"](c5)
         p4 = P["lateral4"](c4, upsample=p5)
         p3 = P["lateral3"](c3, upsample=p4)
+        if self.merged_heads and c5.shape[3] % 64 == 0:
+            # pyramid atlas: the five levels stacked in ONE zero-separated NHWC buffer, so that every head-tower layer is
+            # one launch over all levels instead of five
+            n = c5.shape[0]
+            h6, w6 = (c5.shape[1] - 1) // 2 + 1, (c5.shape[2] - 1) // 2 + 1
+            sizes = ((p3.shape[1], p3.shape[2]), (p4.shape[1], p4.shape[2]), (p5.shape[1], p5.shape[2]), (h6, w6),
+                     ((h6 - 1) // 2 + 1, (w6 - 1) // 2 + 1))
+            at = self._atlas_for(n, sizes, c5.device)
+            v = [engine.AtlasView(at["buf"][0], r, h, w) for r, (h, w) in zip(at["rows"], sizes)]
+            P["smooth3"](p3, out=v[0])
+            P["smooth4"](p4, out=v[1])
+            P["smooth5"](p5, out=v[2])
+            P["pyramid6"](c5, out=v[3])
+            P["pyramid7"](v[3], in_relu=True, out=v[4])
+            return v
         p6 = P["pyramid6"](c5)
         p7 = P["pyramid7"](p6, in_relu=True)
         return [P["smooth3"](p3), P["smooth4"](p4), P["smooth5"](p5), p6, p7]
+
+    def _atlas_for(self, n, sizes, device):
+        """Geometry + persistent, zero-initialised buffers of the pyramid atlas for one batch size / level geometry.
+        Level l occupies rows [rows[l], rows[l] + h_l) x columns [0, w_l); level starts are multiples of 8 (the tile
+        height) with at least one gap row in between; gap rows / columns are never written and stay zero (they ARE the
+        convolutions' zero padding between levels).  tab: every 8 x 16 tile of one image as (row0, col0, row_limit,
+        col_limit)."""
+        key = (n, sizes, str(device))
+        at = self._atlas.get(key)
+        if at is None:
+            rows, r = [], 0
+            for (h, w) in sizes:
+                rows.append(r)
+                r = (r + h + 1 + 7) // 8 * 8
+            ha, wa = rows[-1] + sizes[-1][0], max(w for _, w in sizes)
+            tiles = [(r0 + 8 * ty, 16 * tx, r0 + h, w) for (h, w), r0 in zip(sizes, rows)
+                     for ty in range((h + 7) // 8) for tx in range((w + 15) // 16)]
+            at = {"rows": rows, "ha": ha, "wa": wa, "px": n * sum(h * w for h, w in sizes),
+                  "tab": torch.tensor(tiles, dtype=torch.int32, device=device),
+                  "buf": [torch.zeros((n, ha, wa, 256), dtype=torch.float16, device=device) for _ in range(5)]}
+            self._atlas[key] = at
+        return at
 
     def _heads(self, features, sigmoid=True, sinks=None):
         """Class / box heads on the five levels (odtk/model.py:134-135).  The ten conv chains are
@@ -358,6 +398,8 @@ class Model:
         nl = len(features)
         cls_heads, box_heads = [None] * nl, [None] * nl
         cls_mode = engine.OUT_NCHW_F32_SIGMOID if sigmoid else engine.OUT_NCHW_F32
+        if isinstance(features[0], engine.AtlasView):
+            return self._heads_atlas(features, cls_mode, sinks)
 
         def chain(head, t, final_mode, sink=None):
             for conv in P[head][:-1]:
@@ -393,6 +435,52 @@ class Model:
                 (cls_heads if j == 0 else box_heads)[i] = out
         for ev in joins:
             main.wait_event(ev)
+        return cls_heads, box_heads
+
+    def _heads_atlas(self, views, cls_mode, sinks):
+        """Heads over the pyramid atlas: each of the 4 + 4 tower layers is ONE launch over all five levels (a tile table
+        lists the 8 x 16 tiles of every level; weights are shared between levels anyway, odtk/model.py:134-135); the
+        two final layers run per level on views of the last tower output (their outputs are per-level tensors).  The class
+        and the box tower are independent: two streams / two graph branches."""
+        P = self._packed
+        atlas0 = views[0].atlas
+        sizes = tuple((v.h, v.w) for v in views)
+        at = self._atlas_for(atlas0.shape[0], sizes, atlas0.device)
+        nl = len(views)
+        cls_heads, box_heads = [None] * nl, [None] * nl
+
+        def tower(head, bufs, final_mode, use_sinks):
+            t = atlas0
+            for i, conv in enumerate(P[head][:-1]):
+                nxt = bufs[i & 1]
+                conv(t, relu=True, out=nxt, tile_tab=at["tab"], valid_px=at["px"])
+                t = nxt
+            outs = []
+            for l, v in enumerate(views):
+                lv = engine.AtlasView(t, at["rows"][l], v.h, v.w)
+                if use_sinks is not None:
+                    outs.append(P[head][-1](lv, out_mode=engine.OUT_CANDIDATES, sink=use_sinks[l]))
+                else:
+                    outs.append(P[head][-1](lv, out_mode=final_mode))
+            return outs
+
+        if not self.parallel_heads:
+            cls_heads = tower("cls_head", at["buf"][1:3], cls_mode, sinks)
+            box_heads = tower("box_head", at["buf"][3:5], engine.OUT_NCHW_F32, None)
+            return cls_heads, box_heads
+        main = torch.cuda.current_stream()
+        if self._head_streams is None or len(self._head_streams) < 1:
+            self._head_streams = [torch.cuda.Stream(device=self.device)]
+        side = self._head_streams[0]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            box_heads = tower("box_head", at["buf"][3:5], engine.OUT_NCHW_F32, None)
+            join = torch.cuda.Event()
+            join.record(side)
+        cls_heads = tower("cls_head", at["buf"][1:3], cls_mode, sinks)
+        main.wait_event(join)
         return cls_heads, box_heads
 
     @staticmethod

@@ -275,3 +275,31 @@ def test_full_size_800x1280_resnet50_vs_fp16_oracle(rotated):
     np.testing.assert_array_equal(got[0], os_)
     np.testing.assert_array_equal(got[2], oc)
     np.testing.assert_allclose(got[1], ob, atol=1e-3, rtol=0)
+
+
+@pytest.mark.parametrize("backbone,shape", [("ResNet18FPN", (2, 3, 256, 384)), ("ResNet50FPN", (1, 3, 384, 640))])
+def test_merged_head_launches_over_the_pyramid_atlas_equal_per_level_launches(backbone, shape):
+    """One launch per head-tower layer over all five levels (pyramid atlas + tile table, gap rows as zero padding) must
+    give bit-identical head tensors to the per-level launches: same K order, same fp32 accumulation."""
+    sd = _spread_head(make_state_dict(backbone, 6, 9, False, 31))
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(8)).to(DEV)
+    m = Model(backbone, classes=6).load_state_dict(sd).cuda()
+    assert m.merged_heads
+    c1, b1 = m.forward_heads(x, sigmoid=False)
+    d1 = [t.clone() for t in m(x)]
+    m.merged_heads = False
+    c0, b0 = m.forward_heads(x, sigmoid=False)
+    d0 = m(x)
+    for a, b in zip(c1 + b1, c0 + b0):
+        assert torch.equal(a, b)
+    for a, b in zip(d1, d0):
+        assert torch.equal(a, b)
+    # and the gap rows / columns of the atlas are still zero after the forward passes
+    m.merged_heads = True
+    m.forward_heads(x, sigmoid=False)
+    at = next(iter(m._atlas.values()))
+    for buf in at["buf"]:
+        mask = torch.ones(buf.shape[1:3], dtype=torch.bool, device=buf.device)
+        for r, (h, w) in zip(at["rows"], next(iter(m._atlas.keys()))[1]):
+            mask[r:r + h, :w] = False
+        assert float(buf[:, mask].abs().max()) == 0.0
