@@ -1470,6 +1470,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   p.nstages = kPipeBytes / (kABytes + p.BN * 128);
   if (p.nstages > kMaxStages) p.nstages = kMaxStages;
   p.bias = bias; p.out = y; p.relu = relu; p.out_mode = ODTK_OUT_NHWC_F16; p.ldy = cout; p.ldr = cout;
+  p.oH = OH; p.oR = 0; p.oW = OW;   // dense output (the epilogue addresses pixels through the output view's geometry)
   choose_patch(OH, OW, p.TH, p.TW);
   // raw-window mode: 16 x 8 output-pixel tiles whose A operand is an un-swizzled view of the padded image patch
   static int stem_raw = -1, stem_swap = 0;

@@ -259,8 +259,8 @@ def test_relu_copy():
     ((2, 50, 80, 256, 1024), 1, {"residual": True}, {"mode": 0, "res_mma": 2, "bn": 256, "cluster": 2, "tma_store": 1}),  # deep 1x1: cta_group::2 pairs, residual chunks through the pipeline (R_j * I64)
     ((8, 50, 80, 1024, 256), 1, {}, {"mode": 0, "cluster": 2, "tma_store": 1, "nstages": 6}),
     ((4, 25, 40, 512, 2048), 1, {"residual": True}, {"mode": 0, "cluster": 2, "res_mma": 2}),
-    ((5, 25, 40, 2048, 512), 1, {}, {"mode": 0, "cluster": 2}),                              # odd number of M tiles: padding tile of the last pair
-    ((2, 100, 160, 512, 256), 1, {}, {"mode": 0, "cluster": 0, "tma_store": 1}),             # big-M 1x1 stays unclustered
+    ((19, 25, 40, 2048, 512), 1, {}, {"mode": 0, "cluster": 2, "num_m_tiles": 149}),                              # odd number of M tiles: padding tile of the last pair
+    ((11, 100, 160, 512, 256), 1, {}, {"mode": 0, "cluster": 0, "tma_store": 1}),            # big-M (> 160 000 pixels) 1x1 stays unclustered
     ((2, 200, 320, 256, 64), 1, {}, {"mode": 0, "bn": 64}),
     ((2, 100, 160, 512, 1024), 1, {"stride": 2}, {"mode": 3}),                             # even stride 2: parity split
     ((32, 7, 10, 256, 256), 3, {}, {"mode": 1, "bn": 128}),                                # few tiles: narrower N tile
