@@ -559,7 +559,7 @@ def main():
             # in-step per-layer table: per-launch event times of the LAST eager step (tags: conv 3, small layers 5), joined
             # with the engine trace of one step in launch order
             per = {}
-            for tag, kinds in ((3, ("conv1x1", "conv3x3", "stem7x7", "stem_pool")), (5, ("pad_input", "maxpool", "lower_conv", "relu", "preprocess_u8"))):
+            for tag, kinds in ((3, ("conv1x1", "conv3x3", "stem7x7", "stem_pool", "bneck_tail")), (5, ("pad_input", "maxpool", "lower_conv", "relu", "preprocess_u8"))):
                 tr = [t for t in wl.trace if t["kind"] in kinds]
                 buf = (ctypes.c_float * max(1, len(tr)))()
                 n = lib.odtk_prof_get_list(tag, buf, len(tr)) if tr else 0

@@ -229,6 +229,20 @@ typedef struct {
 int odtk_conv_last_plan(odtk_conv_plan_t *out);
 /* Encoded tensor maps are cached per (base pointer, geometry); hit / miss counters of the process.         */
 int odtk_conv_map_cache_stats(long long *hits, long long *misses);
+/* Tail of a stride-1 ResNet bottleneck block in ONE kernel (torchvision Bottleneck.forward behind
+ * odtk/backbones/resnet.py:24-39; the reference runs it as two cuDNN convolutions + an elementwise add):
+ *     y = relu( conv1x1( relu( conv3x3(x, w2) + b2 ), w3 ) + b3 + residual )
+ * The [n, h, width, c1] output of the 3x3 never leaves the SM (it is rounded to fp16 exactly as the two-kernel route
+ * stores it), and the tensor-bound 3x3 runs under the HBM time of the 1x1 expansion.  c1 in {64, 128}; c2 % 128 == 0,
+ * c2 <= 512; x: NHWC fp16 [n, h, width, c1]; w2: fp16 [c1, 9*c1] (tap-major, channel-minor); w3: fp16 [c2, c1];
+ * b2 / b3: fp32 or NULL; residual, y: NHWC fp16 [n, h, width, c2]; relu: applied to y.                          */
+typedef struct {
+  const void *x, *w2, *w3, *residual;
+  const float *b2, *b3;
+  void *y;
+  int n, h, width, c1, c2, relu;
+} odtk_bneck_t;
+int odtk_bottleneck_tail(const odtk_bneck_t *desc, odtk_stream_t stream);
 /* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */
 int odtk_conv_pack_bias(const float *bias, void *out, int cout, odtk_stream_t stream);
 

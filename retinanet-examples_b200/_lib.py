@@ -61,6 +61,7 @@ SIGNATURES = {
     "odtk_maxpool3x3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]),
     "odtk_stem_conv": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
     "odtk_stem_pool": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "odtk_bottleneck_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "odtk_pad_input": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "odtk_focal_loss": (ctypes.c_longlong, [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_float, ctypes.c_float, ctypes.c_float] + [ctypes.c_void_p] * 4 +
@@ -105,6 +106,14 @@ class ConvPlan(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("mode", "cluster", "bn", "num_m_tiles", "num_n_tiles", "nstages", "npatch",
                                             "tile_t", "b_resident", "bias_mma", "res_mma", "tma_store", "th", "tw", "grid",
                                             "up_mma")]
+
+
+class BneckDesc(ctypes.Structure):
+    """odtk_bneck_t (include/odtk_b200.h)."""
+    _fields_ = [("x", ctypes.c_void_p), ("w2", ctypes.c_void_p), ("w3", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+                ("b2", ctypes.c_void_p), ("b3", ctypes.c_void_p), ("y", ctypes.c_void_p),
+                ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("c1", ctypes.c_int), ("c2", ctypes.c_int),
+                ("relu", ctypes.c_int)]
 
 
 class CandSink(ctypes.Structure):

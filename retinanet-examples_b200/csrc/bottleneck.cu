@@ -1,0 +1,641 @@
+// bottleneck.cu -- the tail of a ResNet bottleneck block in ONE kernel (torchvision Bottleneck.forward, stride 1:
+//     y = relu( conv3_1x1( relu( conv2_3x3(x) + b2 ) ) + b3 + identity )        (BatchNorm folded into w / b)
+// used by odtk/backbones/resnet.py:24-39 through layer1 / layer2).  The reference runs conv2 and conv3 as two cuDNN
+// calls; so did this repo (conv.cu modes 4 and 0).  At 800 x 1280 the 1x1 expansion is HBM-bound (it reads the identity
+// and writes the block output, 4 x C1 channels each) while the 3x3 in front of it is tensor-bound: fused, the 3x3 runs
+// UNDER the expansion's memory time and its [N, H, W, C1] output never touches HBM.
+//
+//   tile      8 rows x 16 columns of pixels per CTA (accumulator row m -> (m % 8, m / 8)), CTA PAIRS (cta_group::2, M = 256)
+//   GEMM1     3x3: the halo patch [18 columns][10-row pitch][64 ch] of a 64-channel chunk is loaded once (one 4-D TMA box,
+//             hardware zero fill == padding); the nine taps are nine shifted SWIZZLE_128B views of it (as conv.cu mode 4).
+//             Accumulator acc1[2] (C1 <= 128 TMEM columns each).
+//   ep1       epilogue warps: acc1 + b2 -> ReLU -> fp16 -> shared memory, written directly in the K-major SWIZZLE_128B
+//             layout of a UMMA A operand ("y1").
+//   GEMM2     1x1: for every 128-channel output tile n2: acc2[n2 & 1] = y1 * W3[n2]^T, then the identity is added ON THE
+//             TENSOR CORE: acc2[:, 64 j ..] += R_j * I^T with R_j the [128 px x 64 ch] identity chunk (A operand, loaded by
+//             TMA straight from the NHWC tensor) and I the 64 x 64 identity matrix.
+//   ep2       acc2 + b3 -> ReLU -> fp16 -> 128B-swizzled slab -> cp.async.bulk.tensor store (4-D box, edges clipped).
+//
+//   warp 0 TMA producer (patches + weights), warp 3 TMA producer of the identity chunks (the HBM stream that bounds the
+//   kernel: its own ring, never blocked behind a weight slot), warp 1 MMA issuer (leader CTA of the pair), warp 2 TMEM
+//   allocator + bias loader, warps 4-11 epilogue.  The issue order is software-pipelined, G1(t+1) before G2(t): the tensor
+//   pipe works on the next tile's 3x3 while the epilogue turns acc1(t) into y1(t).  C1 = 64: both weight matrices stay
+//   resident in shared memory (52 KB per CTA); C1 = 128: they stream through a ring of 8 KB blocks (L2 hits).
+//   The halo patch keeps only the 8 + 2 pixel rows a tile reads (10-slot pitch, 8-row-group stride 1280 B: the 128-byte
+//   swizzle follows the absolute shared-memory address for the TMA write and the UMMA read alike).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "prof.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kNPatch = 2;
+constexpr int kRSlot = 16384;                  // identity chunk: 128 pixels x 64 channels
+constexpr int kMaxRSlots = 4;
+constexpr int kWSlot = 8192;                   // streamed weight block: this CTA's 64 rows x 64 K
+constexpr int kMaxWSlots = 5;
+constexpr int kSlabBytes = 32 * 128;
+constexpr int kIdentBytes = 32 * 128;          // this CTA's 32 rows of the 64 x 64 identity
+constexpr int kBiasBytes = 2560;               // b2 (<= 128 fp32) + b3 (<= 512 fp32)
+constexpr int kBarBytes = 512;
+constexpr int kTmemCols = 512;
+constexpr int kSmemMax = 232448;               // 227 KB
+
+// Optional in-kernel wait profile (build with -DODTK_BT_PROF, tools only): cycles each role of CTA 0 spends in its waits.
+#ifdef ODTK_BT_PROF
+__device__ unsigned long long g_bt_prof[32];
+#define BT_WAIT(cat, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_bt_prof[cat], (unsigned long long)(clock64() - t0_)); } while (0)
+#define BT_T0(name) const long long name = clock64()
+#define BT_ADD(cat, name) do { if (blockIdx.x == 0 && lane == 0 && warp == 4) atomicAdd(&g_bt_prof[cat], (unsigned long long)(clock64() - name)); } while (0)
+#define BT_TOTAL_BEGIN() const long long tt0_ = clock64()
+#define BT_TOTAL_END(cat) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_bt_prof[cat], (unsigned long long)(clock64() - tt0_)); } while (0)
+#else
+#define BT_WAIT(cat, bar, par) mbar_wait(bar, par)
+#define BT_T0(name)
+#define BT_ADD(cat, name)
+#define BT_TOTAL_BEGIN()
+#define BT_TOTAL_END(cat)
+#endif
+
+struct BtBars {
+  uint64_t pfull[kNPatch], pempty[kNPatch];
+  uint64_t wfull[kMaxWSlots], wempty[kMaxWSlots];
+  uint64_t rfull[kMaxRSlots], rempty[kMaxRSlots];
+  uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t acc2_full[2], acc2_empty[2];
+  uint64_t y1_full[2], y1_empty[2], ident_full, wres_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(BtBars) <= kBarBytes, "barrier block too small");
+
+struct BtParams {
+  int N, H, W, C1, C2;
+  int tiles_h, tiles_w, total_tiles;
+  int ppitch;            // pixel slots per patch column: 16, or 10 (only the 8 + 2 rows a tile reads)
+  int patch_slot;        // bytes between patch buffers (1024-aligned)
+  int w_resident;        // C1 == 64: W2 / W3 halves stay in shared memory (52 KB); else they stream through the weight ring
+  int nw, nr;            // weight / identity ring depths
+  int relu;
+  const float *b2, *b3;
+};
+
+// halo view (conv.cu make_desc_halo): 8-row groups (8 consecutive pixels of a patch column) `sbo` bytes apart
+__device__ __forceinline__ uint64_t bt_desc_halo(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2,
+                       const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmR,
+                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmI,
+                       const __grid_constant__ BtParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // layout (every region 1024-aligned): patches | weights (resident, or ring) | identity ring | y1 | ident | slabs | bias | barriers
+  const int kc1 = p.C1 >> 6;                         // 64-channel chunks of the 3x3's input == of y1
+  const int n2tiles = p.C2 >> 7;
+  const uint32_t w2_block = (uint32_t)(p.C1 >> 1) * 128u;    // this CTA's half of the rows of one W2 block (tap, chunk)
+  const int nb1 = 9 * kc1;                           // W2 blocks per tile, linear index b = chunk * 9 + tap
+  unsigned char *spatch = smem;
+  unsigned char *sw = spatch + kNPatch * p.patch_slot;
+  const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot : (uint32_t)p.nw * kWSlot;
+  unsigned char *sres = sw + w_bytes;
+  unsigned char *sy1 = sres + p.nr * kRSlot;
+  unsigned char *sident = sy1 + 2 * kc1 * 16384;    // y1 is double-buffered: ep1(t+1) does not wait for GEMM2(t)
+  unsigned char *sslab = sident + kIdentBytes;
+  float *sbias = reinterpret_cast<float *>(sslab + kEpiWarps * kSlabBytes);
+  BtBars *bars = reinterpret_cast<BtBars *>(reinterpret_cast<unsigned char *>(sbias) + kBiasBytes);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const uint32_t patch_bytes = 18u * (uint32_t)p.ppitch * 128u;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kNPatch; s++) { mbar_init(&bars->pfull[s], 1); mbar_init(&bars->pempty[s], 1); }
+    for (int s = 0; s < kMaxWSlots; s++) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+    for (int s = 0; s < kMaxRSlots; s++) { mbar_init(&bars->rfull[s], 1); mbar_init(&bars->rempty[s], 1); }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 2 * kEpiWarps);   // one arrival per epilogue warp of the pair
+      mbar_init(&bars->acc2_full[b], 1); mbar_init(&bars->acc2_empty[b], 2 * kEpiWarps);
+      mbar_init(&bars->y1_full[b], 2 * kEpiWarps); mbar_init(&bars->y1_empty[b], 1);
+    }
+    mbar_init(&bars->ident_full, 1); mbar_init(&bars->wres_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    for (int i = lane; i < p.C1; i += 32) sbias[i] = p.b2 ? p.b2[i] : 0.0f;
+    for (int i = lane; i < p.C2; i += 32) sbias[128 + i] = p.b3 ? p.b3[i] : 0.0f;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // work: pairs of consecutive tiles; the pair's second tile may be padding (odd total): computed, never stored
+  const int npairs = (p.total_tiles + 1) >> 1;
+  const int c_first = (int)(blockIdx.x >> 1), c_step = (int)(gridDim.x >> 1);
+  const int per_img = p.tiles_h * p.tiles_w;
+  auto tile_of = [&](int pair, int &img, int &h0, int &w0) -> bool {
+    int t = 2 * pair + crank;
+    const bool real = t < p.total_tiles;
+    if (!real) t = p.total_tiles - 1;
+    img = t / per_img;
+    const int rr = t - img * per_img;
+    h0 = (rr / p.tiles_w) * 8;
+    w0 = (rr % p.tiles_w) * 16;
+    return real;
+  };
+
+  if (warp == 0) {
+    // ============================ TMA producer: patches + weights ============================
+    int ws = 0, pb = 0;
+    uint32_t wph = 0, pphase = 0;
+    if (elect_one()) {
+      if (crank == 0) mbar_arrive_expect_tx(&bars->ident_full, 2u * kIdentBytes);
+      tma2_load_2d(sident, &tmI, mapa_rank(smem_u32(&bars->ident_full), 0), 0, 32 * crank);
+    }
+    if (p.w_resident && elect_one()) {
+      const uint32_t lbar = mapa_rank(smem_u32(&bars->wres_full), 0);
+      if (crank == 0) mbar_arrive_expect_tx(&bars->wres_full, 2u * w_bytes);
+      for (int i = 0; i < nb1; i++) {
+        const int kc = i / 9, tap = i - 9 * kc;
+        tma2_load_2d(sw + i * w2_block, &tmW2, lbar, tap * p.C1 + kc * 64, crank * (p.C1 >> 1));
+      }
+      for (int n2 = 0; n2 < n2tiles; n2++)
+        for (int kc = 0; kc < kc1; kc++)
+          tma2_load_2d(sw + nb1 * w2_block + (n2 * kc1 + kc) * kWSlot, &tmW3, lbar, kc * 64, n2 * 128 + crank * 64);
+    }
+    auto produce_g1 = [&](int pair) {
+      int img, h0, w0;
+      tile_of(pair, img, h0, w0);
+      for (int kc = 0; kc < kc1; kc++) {
+        BT_WAIT(7, &bars->pempty[pb], pphase ^ 1u);
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&bars->pfull[pb], 2u * patch_bytes);
+          tma2_load_4d(spatch + pb * p.patch_slot, &tmX, mapa_rank(smem_u32(&bars->pfull[pb]), 0), kc * 64, h0 - 1, w0 - 1, img);
+        }
+        if (++pb == kNPatch) { pb = 0; pphase ^= 1u; }
+        if (p.w_resident) continue;
+        for (int tap = 0; tap < 9; tap++) {
+          BT_WAIT(8, &bars->wempty[ws], wph ^ 1u);
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(&bars->wfull[ws], 2u * w2_block);
+            tma2_load_2d(sw + ws * kWSlot, &tmW2, mapa_rank(smem_u32(&bars->wfull[ws]), 0), tap * p.C1 + kc * 64, crank * (p.C1 >> 1));
+          }
+          if (++ws == p.nw) { ws = 0; wph ^= 1u; }
+        }
+      }
+    };
+    auto produce_g2 = [&]() {
+      if (p.w_resident) return;
+      for (int n2 = 0; n2 < n2tiles; n2++)
+        for (int kc = 0; kc < kc1; kc++) {
+          BT_WAIT(8, &bars->wempty[ws], wph ^ 1u);
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(&bars->wfull[ws], 2u * (uint32_t)kWSlot);
+            tma2_load_2d(sw + ws * kWSlot, &tmW3, mapa_rank(smem_u32(&bars->wfull[ws]), 0), kc * 64, n2 * 128 + crank * 64);
+          }
+          if (++ws == p.nw) { ws = 0; wph ^= 1u; }
+        }
+    };
+    BT_TOTAL_BEGIN();
+    if (c_first < npairs) produce_g1(c_first);
+    for (int pair = c_first; pair < npairs; pair += c_step) {
+      if (pair + c_step < npairs) produce_g1(pair + c_step);
+      produce_g2();
+    }
+    BT_TOTAL_END(9);
+  } else if (warp == 3) {
+    // ============================ TMA producer: the identity stream (HBM) ============================
+    int rs = 0;
+    uint32_t rph = 0;
+    BT_TOTAL_BEGIN();
+    for (int pair = c_first; pair < npairs; pair += c_step) {
+      int img, h0, w0;
+      tile_of(pair, img, h0, w0);
+      for (int c = 0; c < 2 * n2tiles; c++) {
+        BT_WAIT(10, &bars->rempty[rs], rph ^ 1u);
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&bars->rfull[rs], 2u * (uint32_t)kRSlot);
+          tma2_load_4d(sres + rs * kRSlot, &tmR, mapa_rank(smem_u32(&bars->rfull[rs]), 0), c * 64, h0, w0, img);
+        }
+        if (++rs == p.nr) { rs = 0; rph ^= 1u; }
+      }
+    }
+    BT_TOTAL_END(11);
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA) ===========================
+    if (crank == 0) {
+      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(p.C1 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc_r = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t w_s = smem_u32(sw), res_s = smem_u32(sres), patch_s = smem_u32(spatch), y1_s = smem_u32(sy1), ident_s = smem_u32(sident);
+      const uint32_t sbo = (uint32_t)p.ppitch * 128u;
+      int ws = 0, rs = 0, pb = 0;
+      uint32_t wph = 0, rph = 0, pphase = 0;
+      int it1 = 0, it2 = 0, u2 = 0;                  // G1 / G2 invocation counters, acc2 use counter
+      mbar_wait(&bars->ident_full, 0);
+      if (p.w_resident) mbar_wait(&bars->wres_full, 0);
+      tc_fence_after();
+      auto issue_g1 = [&]() {
+        const int buf = it1 & 1;
+        BT_WAIT(0, &bars->acc1_empty[buf], ((uint32_t)(it1 >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 128);
+        for (int kc = 0; kc < kc1; kc++) {
+          BT_WAIT(1, &bars->pfull[pb], pphase);
+          tc_fence_after();
+          const uint32_t pbase = patch_s + (uint32_t)(pb * p.patch_slot);
+          for (int tap = 0; tap < 9; tap++) {
+            uint32_t wb;
+            if (p.w_resident) wb = w_s + (uint32_t)(kc * 9 + tap) * w2_block;
+            else {
+              BT_WAIT(2, &bars->wfull[ws], wph);
+              tc_fence_after();
+              wb = w_s + (uint32_t)(ws * kWSlot);
+            }
+            const int r = tap / 3, s3 = tap - 3 * r;
+            const uint64_t da = bt_desc_halo(pbase + (uint32_t)(s3 * p.ppitch + r) * 128u, sbo);
+            const uint64_t db = make_desc_kmajor(wb, 128);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kc | tap | k) ? 1u : 0u);
+              if (!p.w_resident) tc_commit2_mc(&bars->wempty[ws], (uint16_t)3);
+              if (tap == 8) tc_commit2_mc(&bars->pempty[pb], (uint16_t)3);
+            }
+            if (!p.w_resident) { if (++ws == p.nw) { ws = 0; wph ^= 1u; } }
+          }
+          if (++pb == kNPatch) { pb = 0; pphase ^= 1u; }
+        }
+        if (elect_one()) tc_commit2_mc(&bars->acc1_full[buf], (uint16_t)3);
+        it1++;
+      };
+      auto issue_g2 = [&]() {
+        const int yb = it2 & 1;
+        BT_WAIT(3, &bars->y1_full[yb], (uint32_t)(it2 >> 1) & 1u);
+        tc_fence_after();
+        for (int n2 = 0; n2 < n2tiles; n2++, u2++) {
+          const int buf = u2 & 1;
+          BT_WAIT(4, &bars->acc2_empty[buf], ((uint32_t)(u2 >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + 256u + (uint32_t)(buf * 128);
+          for (int kc = 0; kc < kc1; kc++) {
+            uint32_t wb;
+            if (p.w_resident) wb = w_s + (uint32_t)nb1 * w2_block + (uint32_t)(n2 * kc1 + kc) * kWSlot;
+            else {
+              BT_WAIT(2, &bars->wfull[ws], wph);
+              tc_fence_after();
+              wb = w_s + (uint32_t)(ws * kWSlot);
+            }
+            const uint64_t da = make_desc_kmajor(y1_s + (uint32_t)(yb * kc1 + kc) * 16384u, 128);
+            const uint64_t db = make_desc_kmajor(wb, 128);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kc | k) ? 1u : 0u);
+              if (!p.w_resident) tc_commit2_mc(&bars->wempty[ws], (uint16_t)3);
+            }
+            if (!p.w_resident) { if (++ws == p.nw) { ws = 0; wph ^= 1u; } }
+          }
+          for (int j = 0; j < 2; j++) {
+            BT_WAIT(5, &bars->rfull[rs], rph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = make_desc_kmajor(res_s + (uint32_t)(rs * kRSlot), 128);
+              const uint64_t db = make_desc_kmajor(ident_s, 128);
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_r, 1u);
+              tc_commit2_mc(&bars->rempty[rs], (uint16_t)3);
+            }
+            if (++rs == p.nr) { rs = 0; rph ^= 1u; }
+          }
+          if (elect_one()) tc_commit2_mc(&bars->acc2_full[buf], (uint16_t)3);
+        }
+        if (elect_one()) tc_commit2_mc(&bars->y1_empty[yb], (uint16_t)3);
+        it2++;
+      };
+      BT_TOTAL_BEGIN();
+      if (c_first < npairs) issue_g1();
+      for (int pair = c_first; pair < npairs; pair += c_step) {
+        if (pair + c_step < npairs) issue_g1();
+        issue_g2();
+      }
+      BT_TOTAL_END(6);
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==========================================
+    const int q = warp & 3, sg = (warp - 4) >> 2;
+    const int row = q * 32 + lane;                   // accumulator row == pixel (row % 8, row / 8) of the tile
+    const uint32_t slab_s = smem_u32(sslab + (warp - 4) * kSlabBytes);
+    const uint32_t y1_s = smem_u32(sy1), sb_s = smem_u32(sbias);
+    const uint32_t lbar_acc1e0 = mapa_rank(smem_u32(&bars->acc1_empty[0]), 0), lbar_acc1e1 = mapa_rank(smem_u32(&bars->acc1_empty[1]), 0);
+    const uint32_t lbar_acc2e0 = mapa_rank(smem_u32(&bars->acc2_empty[0]), 0), lbar_acc2e1 = mapa_rank(smem_u32(&bars->acc2_empty[1]), 0);
+    const uint32_t lbar_y1f0 = mapa_rank(smem_u32(&bars->y1_full[0]), 0), lbar_y1f1 = mapa_rank(smem_u32(&bars->y1_full[1]), 0);
+    const int cols1 = p.C1 >> 1;                     // columns of acc1 this warp converts: [sg * cols1, +cols1)
+    // ---- ep1: acc1 + b2 -> ReLU -> fp16 -> y1 (K-major, 128-byte swizzle: the A operand of GEMM2) ----
+    auto ep1 = [&](int it) {
+      const int buf = it & 1;
+      BT_WAIT(12, &bars->acc1_full[buf], (uint32_t)(it >> 1) & 1u);
+      BT_WAIT(13, &bars->y1_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + sg * cols1);
+      const uint32_t yrow = y1_s + (uint32_t)(buf * kc1) * 16384u + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+      uint32_t v[2][16];
+      const int nch = cols1 >> 4;                    // 16-column chunks: 2 (C1 = 64) or 4 (C1 = 128)
+      tc_ld16(taddr, v[0]);
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        if (cc < nch) {
+          tc_ld_wait();
+          if (cc + 1 < nch) tc_ld16(taddr + (uint32_t)((cc + 1) * 16), v[(cc + 1) & 1]);
+          const int col0 = sg * cols1 + cc * 16;     // first of the 16 channels of this chunk
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128f(sb_s + (uint32_t)((col0 + j4 * 4) * 4));
+            f[4 * j4] = __uint_as_float(v[cc & 1][4 * j4]) + b.x;
+            f[4 * j4 + 1] = __uint_as_float(v[cc & 1][4 * j4 + 1]) + b.y;
+            f[4 * j4 + 2] = __uint_as_float(v[cc & 1][4 * j4 + 2]) + b.z;
+            f[4 * j4 + 3] = __uint_as_float(v[cc & 1][4 * j4 + 3]) + b.w;
+          }
+          uint4 o0, o1;
+          __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
+          const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            q0[j] = __hmax2(__floats2half2_rn(f[2 * j], f[2 * j + 1]), z);
+            q1[j] = __hmax2(__floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]), z);
+          }
+          const int kc = col0 >> 6, unit = (col0 & 63) >> 3;
+          const uint32_t base = yrow + (uint32_t)kc * 16384u;
+          sts128(base + (uint32_t)(((unit) ^ (row & 7)) << 4), o0);
+          sts128(base + (uint32_t)(((unit + 1) ^ (row & 7)) << 4), o1);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                               // ONE arrival per warp: 512 remote arrivals per barrier serialise on it
+        mbar_arrive_remote(buf ? lbar_acc1e1 : lbar_acc1e0);
+        mbar_arrive_remote(buf ? lbar_y1f1 : lbar_y1f0);
+      }
+    };
+    int u2 = 0;
+    // ---- ep2: per 128-channel output tile: acc2 (+ identity, added by the tensor core) + b3 -> ReLU -> fp16 -> store ----
+    auto ep2 = [&](int pair) {
+      int img, h0, w0;
+      const bool real = tile_of(pair, img, h0, w0);
+      for (int n2 = 0; n2 < n2tiles; n2++, u2++) {
+        const int buf = u2 & 1;
+        BT_WAIT(14, &bars->acc2_full[buf], (uint32_t)(u2 >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(buf * 128 + sg * 64);
+        BT_T0(ta_);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the slab
+        __syncwarp();
+        BT_ADD(17, ta_);
+        BT_T0(tb_);
+        const uint32_t srow = slab_s + (uint32_t)(lane * 128);
+        uint32_t v[2][16];
+        tc_ld16(taddr, v[0]);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          tc_ld_wait();
+          if (cc < 3) tc_ld16(taddr + (uint32_t)((cc + 1) * 16), v[(cc + 1) & 1]);
+          const int col0 = n2 * 128 + sg * 64 + cc * 16;
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128f(sb_s + (uint32_t)((128 + col0 + j4 * 4) * 4));
+            f[4 * j4] = __uint_as_float(v[cc & 1][4 * j4]) + b.x;
+            f[4 * j4 + 1] = __uint_as_float(v[cc & 1][4 * j4 + 1]) + b.y;
+            f[4 * j4 + 2] = __uint_as_float(v[cc & 1][4 * j4 + 2]) + b.z;
+            f[4 * j4 + 3] = __uint_as_float(v[cc & 1][4 * j4 + 3]) + b.w;
+          }
+          uint4 o0, o1;
+          __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+          }
+          if (p.relu) {
+            const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
+          }
+          sts128(srow + (uint32_t)(((2 * cc) ^ (lane & 7)) << 4), o0);
+          sts128(srow + (uint32_t)(((2 * cc + 1) ^ (lane & 7)) << 4), o1);
+        }
+        BT_ADD(18, tb_);
+        BT_T0(tc_);
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        BT_ADD(19, tc_);
+        BT_T0(td_);
+        if (lane == 0) {
+          mbar_arrive_remote(buf ? lbar_acc2e1 : lbar_acc2e0);   // the accumulator is in the slab: hand it back (one arrival per warp)
+          if (real) {
+            // 32 pixels = 8 rows x 4 columns of the tile; pixels outside the image are clipped by the TMA unit
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tmY), "r"(slab_s), "r"(n2 * 128 + sg * 64), "r"(h0), "r"(w0 + 4 * q), "r"(img)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        __syncwarp();
+        BT_ADD(20, td_);
+      }
+    };
+    // software pipeline, mirrored by the MMA warp: ep1(t+1) (feeds GEMM2(t+1)) before ep2(t)
+    int it = 0;
+    BT_TOTAL_BEGIN();
+    if (c_first < npairs) ep1(it++);
+    for (int pair = c_first; pair < npairs; pair += c_step) {
+      if (pair + c_step < npairs) ep1(it++);
+      ep2(pair);
+    }
+    if (warp == 4) { BT_TOTAL_END(16); }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA may leave while its peer can still write to it / read its shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool bt_encode(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides, const uint32_t *box) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return false;
+    fn = (EncodeTiledFn)ptr;
+  }
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; i++) gstr[i] = strides[i];
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __half g_bt_ident[64 * 64];
+__global__ void bt_init_ident_kernel() {
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) g_bt_ident[i] = __float2half_rn((i >> 6) == (i & 63) ? 1.0f : 0.0f);
+}
+
+struct BtDevice { bool ready; void *ident; };
+BtDevice g_bt_dev[64];
+std::mutex g_bt_mu;
+
+const BtDevice *bt_device(cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_bt_mu);
+  BtDevice &d = g_bt_dev[dev];
+  if (d.ready) return &d;
+  if (cudaFuncSetAttribute(bottleneck_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) return nullptr;
+  if (cudaGetSymbolAddress(&d.ident, g_bt_ident) != cudaSuccess) return nullptr;
+  bt_init_ident_kernel<<<1, 256, 0, stream>>>();
+  if (cudaGetLastError() != cudaSuccess) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+  }
+  d.ready = true;
+  return &d;
+}
+
+}  // namespace
+
+#ifdef ODTK_BT_PROF
+extern "C" int odtk_bt_prof_read(unsigned long long *out, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return ODTK_E_CUDA;
+  if (cudaMemcpyFromSymbol(out, g_bt_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return ODTK_E_CUDA;
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_bt_prof, z, sizeof z); }
+  return ODTK_OK;
+}
+#endif
+
+extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_) {
+  if (!d || !d->x || !d->w2 || !d->w3 || !d->residual || !d->y) return ODTK_E_INVALID;
+  if (d->n <= 0 || d->h <= 0 || d->width <= 0) return ODTK_E_INVALID;
+  if ((d->c1 != 64 && d->c1 != 128) || d->c2 % 128 != 0 || d->c2 <= 0 || d->c2 > 512) return ODTK_E_UNSUPPORTED;
+  if (((uintptr_t)d->x | (uintptr_t)d->w2 | (uintptr_t)d->w3 | (uintptr_t)d->residual | (uintptr_t)d->y) & 15) return ODTK_E_INVALID;
+  if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BtDevice *ds = bt_device(stream);
+  if (!ds) return ODTK_E_CUDA;
+  BtParams p;
+  memset(&p, 0, sizeof p);
+  p.N = d->n; p.H = d->h; p.W = d->width; p.C1 = d->c1; p.C2 = d->c2;
+  p.tiles_h = (d->h + 7) / 8; p.tiles_w = (d->width + 15) / 16;
+  const long long total = (long long)d->n * p.tiles_h * p.tiles_w;
+  if (total >= (1ll << 30)) return ODTK_E_UNSUPPORTED;
+  p.total_tiles = (int)total;
+  static int pitch = -1, nr_cap = -1;
+  if (pitch < 0) {
+    const char *e = getenv("ODTK_BNECK_PITCH"); pitch = (e && atoi(e) == 16) ? 16 : 10;
+    const char *r = getenv("ODTK_BNECK_NR"); nr_cap = r ? atoi(r) : kMaxRSlots;
+    if (nr_cap < 2 || nr_cap > kMaxRSlots) nr_cap = kMaxRSlots;
+  }
+  p.ppitch = pitch;
+  p.patch_slot = (18 * pitch * 128 + 1023) / 1024 * 1024;
+  p.w_resident = d->c1 == 64;
+  const int kc1 = d->c1 / 64, n2tiles = d->c2 / 128;
+  const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot;
+  if (p.w_resident && w_resident_bytes > 60 * 1024) p.w_resident = 0;
+  const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kIdentBytes + kEpiWarps * kSlabBytes + kBiasBytes + kBarBytes;
+  // shared-memory budget: identity ring as deep as it gets (it carries the HBM stream), then the weight ring
+  p.nw = p.w_resident ? 0 : 4;
+  int left = kSmemMax - fixed - (p.w_resident ? w_resident_bytes : p.nw * kWSlot);
+  p.nr = left / kRSlot;
+  if (p.nr > nr_cap) p.nr = nr_cap;
+  if (p.nr < 2) return ODTK_E_UNSUPPORTED;
+  left -= p.nr * kRSlot;
+  if (!p.w_resident) { p.nw += left / kWSlot; if (p.nw > kMaxWSlots) p.nw = kMaxWSlots; }
+  const int smem_bytes = fixed + (p.w_resident ? w_resident_bytes : p.nw * kWSlot) + p.nr * kRSlot;
+  p.relu = d->relu;
+  p.b2 = d->b2; p.b3 = d->b3;
+  const uint64_t C1 = (uint64_t)d->c1, C2 = (uint64_t)d->c2, H = (uint64_t)d->h, W = (uint64_t)d->width, N = (uint64_t)d->n;
+  CUtensorMap tmX, tmW2, tmW3, tmR, tmY, tmI;
+  {
+    uint64_t dims[4] = {C1, H, W, N}, str[3] = {W * C1 * 2, C1 * 2, H * W * C1 * 2};
+    uint32_t box[4] = {64, (uint32_t)p.ppitch, 18, 1};
+    if (!bt_encode(&tmX, d->x, 4, dims, str, box)) return ODTK_E_CUDA;
+  }
+  {
+    uint64_t dims[2] = {9 * C1, C1}, str[1] = {9 * C1 * 2};
+    uint32_t box[2] = {64, (uint32_t)(d->c1 / 2)};
+    if (!bt_encode(&tmW2, d->w2, 2, dims, str, box)) return ODTK_E_CUDA;
+  }
+  {
+    uint64_t dims[2] = {C1, C2}, str[1] = {C1 * 2};
+    uint32_t box[2] = {64, 64};
+    if (!bt_encode(&tmW3, d->w3, 2, dims, str, box)) return ODTK_E_CUDA;
+  }
+  {
+    uint64_t dims[4] = {C2, H, W, N}, str[3] = {W * C2 * 2, C2 * 2, H * W * C2 * 2};
+    uint32_t boxR[4] = {64, 8, 16, 1}, boxY[4] = {64, 8, 4, 1};
+    if (!bt_encode(&tmR, d->residual, 4, dims, str, boxR) || !bt_encode(&tmY, d->y, 4, dims, str, boxY)) return ODTK_E_CUDA;
+  }
+  {
+    uint64_t dims[2] = {64, 64}, str[1] = {128};
+    uint32_t box[2] = {64, 32};
+    if (!bt_encode(&tmI, ds->ident, 2, dims, str, box)) return ODTK_E_CUDA;
+  }
+  const int sms = odtk_sm_count();
+  const int npairs = (p.total_tiles + 1) / 2;
+  int clusters = sms / 2;
+  if (clusters > npairs) clusters = npairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    OdtkProfScope prof(ODTK_PROF_CONV, stream);
+    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmI, p);
+  }
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}

@@ -298,9 +298,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           h0 = (r / p.tiles_w) * p.TH;
           w0 = (r % p.tiles_w) * p.TW;
         }
-        for (int tap = 0; tap < p.taps; tap++) {
-          const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
-          for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
+        // K order: 64-channel chunk outer, tap inner -- the same order as the halo mode, so that a layer's result does not
+        // depend on which A-operand mode / tile shape the host code picked (fp32 sums are order-sensitive)
+        for (int kb = 0; kb < p.kblocks_per_tap; kb++) {
+          for (int tap = 0; tap < p.taps; tap++) {
+            const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             unsigned char *sa = smem + stage * kStageBytes;
             unsigned char *sb = sa + kABytes;
@@ -1166,7 +1168,12 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     long long mt = (opix + 127) / 128;
     if (d->ksize == 3 && st == 1) mt = (long long)d->n * ((d->h + 15) / 16) * ((d->width + 7) / 8);   // halo tiles (upper bound)
     const int sms = odtk_sm_count();
-    while (shrink_on && groups == 1 && d->out_mode == ODTK_OUT_NHWC_F16 && !d->upsample && !d->residual && BN > 64 && (BN % 32) == 0 &&
+    // K-heavy layers on few tiles (FPN pyramid6: 3x3 s2 2048 -> 256 on 13 x 20) are bound by the operand stream from L2,
+    // not by the number of busy SMs: 1 = halve N but run cta_group::2 pairs, 2 = keep N = 256 and pair
+    static int kheavy = -1;
+    if (kheavy < 0) { const char *e = getenv("ODTK_CONV_KHEAVY"); kheavy = e ? atoi(e) : 2; }
+    const bool k_heavy = kheavy && (long long)d->ksize * d->ksize * d->cin >= 8192;
+    while (shrink_on && !(k_heavy && kheavy >= 2) && groups == 1 && d->out_mode == ODTK_OUT_NHWC_F16 && !d->upsample && !d->residual && BN > 64 && (BN % 32) == 0 &&
            d->cout % (BN / 2) == 0 && mt * ((d->cout + BN - 1) / BN) * 2 <= sms)
       BN /= 2;
   }
@@ -1277,7 +1284,11 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
     const double eff_a = hw / ((double)((d->h + 15) / 16) * ((d->width + 7) / 8) * 128.0);
     const double eff_b = hw / ((double)((d->h + 7) / 8) * ((d->width + 15) / 16) * 128.0);
     // row-major tiles keep the fp32 NCHW stores of the head outputs in 32-byte runs: prefer them there
-    const bool transposed = (p.out_mode == ODTK_OUT_NHWC_F16) ? eff_b > eff_a + 1e-9 : eff_b > 1.15 * eff_a;
+    // (the candidate-append epilogue writes no dense map either: it takes whichever tiling wastes fewer rows)
+    static int cand_t = -1;
+    if (cand_t < 0) { const char *e = getenv("ODTK_CONV_CAND_T"); cand_t = e ? atoi(e) : 1; }
+    const bool dense_f32 = p.out_mode == ODTK_OUT_NCHW_F32 || p.out_mode == ODTK_OUT_NCHW_F32_SIGMOID || (p.out_mode == ODTK_OUT_CANDIDATES && !cand_t);
+    const bool transposed = !dense_f32 ? eff_b > eff_a + 1e-9 : eff_b > 1.15 * eff_a;
     const double eff_halo = transposed ? eff_b : eff_a;
     // narrow N (head outputs with few channels): the per-tap A re-load of mode 1 dominates, take the halo tiles anyway
     if (d->tile_tab || (halo_on && (eff_halo >= 0.84 * eff_free || (BN <= 64 && eff_halo >= 0.6 * eff_free)) && d->h >= 8 && d->width >= 8)) {
@@ -1321,7 +1332,10 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   CUtensorMap tmOnes = tmB, tmBias = tmB;
   static int bias_mma_on = -1;
   if (bias_mma_on < 0) { const char *e = getenv("ODTK_CONV_BIAS_MMA"); bias_mma_on = e ? atoi(e) : 1; }
-  if (bias_mma_on && d->bias_op && d->bias) {
+  static int deep_bias_epi = -1;
+  if (deep_bias_epi < 0) { const char *e = getenv("ODTK_CONV_DEEP_BIAS_EPI"); deep_bias_epi = e ? atoi(e) : 1; }   // measured: 512 -> 2048 +res 88.5 -> 81.6 us, others within noise
+  const bool deep_layer = d->ksize == 1 && stride == 1 && BN == 256 && d->cin >= 256 && p.M <= 160000 && p.out_mode == ODTK_OUT_NHWC_F16 && !d->upsample;
+  if (bias_mma_on && d->bias_op && d->bias && !(deep_bias_epi && deep_layer)) {
     const void *ones = dstate->ones;
     uint64_t dimsO[2] = {64, 128}, strO[1] = {128};
     uint32_t boxO[2] = {64, 128};
@@ -1348,10 +1362,18 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   if (deep_1x1 < 0) { const char *e = getenv("ODTK_CONV_DEEP_1X1"); deep_1x1 = e ? atoi(e) : 1; }
   const bool deep_pair = deep_1x1 && cluster_on >= 2 && p.mode == 0 && BN == 256 && d->cin >= 256 && p.M <= 160000 &&
                          p.out_mode == ODTK_OUT_NHWC_F16 && !d->upsample;
-  if (cluster_on && (BN > 128 || narrow_pair) && !d->upsample && (!d->residual || res_pair || deep_pair) &&
+  // 128-wide 3x3 layers (ResNet layer2's conv2): a 128 x 128 tile streams 16 KB of weights per 256 tensor-core cycles --
+  // as cta_group::2 pairs each CTA fetches half of that
+  static int two_128 = -1;
+  if (two_128 < 0) { const char *e = getenv("ODTK_CONV_TWO_128"); two_128 = e ? atoi(e) : 1; }
+  const bool mid_pair = two_128 && cluster_on >= 2 && d->ksize == 3 && BN == 128 && p.out_mode == ODTK_OUT_NHWC_F16 && groups == 1;
+  static int kheavy2 = -1;
+  if (kheavy2 < 0) { const char *e = getenv("ODTK_CONV_KHEAVY"); kheavy2 = e ? atoi(e) : 2; }
+  const bool k_heavy2 = kheavy2 && (long long)d->ksize * d->ksize * d->cin >= 8192 && cluster_on >= 2 && BN >= 128;
+  if (cluster_on && (BN > 128 || narrow_pair || mid_pair || k_heavy2) && !d->upsample && (!d->residual || res_pair || deep_pair) &&
       (cluster_1x1 || d->ksize == 3 || res_pair || deep_pair) &&
       (p.mode == 0 || p.mode == 1 || p.mode == 3 || (p.mode == 4 && cluster_on >= 2)) &&
-      ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= g_num_sms / 2 && (BN / 2) % 8 == 0) {
+      ((p.num_m_tiles + 1) / 2) * p.num_n_tiles >= (k_heavy2 ? g_num_sms / 8 : g_num_sms / 2) && (BN / 2) % 8 == 0) {
     const uint64_t Kw = (uint64_t)p.taps * d->cin;
     uint64_t dims[2] = {Kw, (uint64_t)d->cout}, str[1] = {Kw * 2};
     uint32_t box[2] = {64, (uint32_t)(BN / 2)};

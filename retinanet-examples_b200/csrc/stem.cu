@@ -35,7 +35,11 @@ constexpr int kPatchSlot = 12288;
 constexpr int kCout = 64;
 constexpr int kWBytes = 7 * kCout * 64;              // 7 filter rows x [64 cout x 32 k] fp16 (SWIZZLE_64B rows)
 constexpr int kStageTile = 256 * 128;                // staging: 16 x 16 stem pixels x 64 ch fp16
-constexpr int kEpiWarps = 8;
+#ifndef ODTK_STEM_EPI_WARPS
+#define ODTK_STEM_EPI_WARPS 16   /* 8: each warp converts 64 columns; 16: 32 columns (the epilogue, not the 28 MMAs, bounds a tile) */
+#endif
+constexpr int kEpiWarps = ODTK_STEM_EPI_WARPS;
+constexpr int kColSplit = kEpiWarps / 8;             // warps sharing one (lane quarter, half) accumulator: each takes 64 / kColSplit columns
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kTmemCols = 256;                       // 2 buffers x (2 halves x 64 columns)
 constexpr int kPool = 7;                             // pooled pixels per tile side
@@ -144,11 +148,11 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, half = ((warp - 4) >> 2) & 1, cpart = (warp - 4) >> 3;   // cpart: which 64 / kColSplit columns
     const int m = q * 32 + lane;                 // accumulator row
     const int si = m >> 3, sj = half * 8 + (m & 7);   // stem pixel of this thread inside the 16 x 16 tile
     const int pix = si * 16 + sj;
-    const int et = (warp - 4) * 32 + lane;       // 0 .. 255
+    const int et = (warp - 4) * 32 + lane;       // 0 .. 32 * kEpiWarps - 1
     const uint32_t sbias_s = smem_u32(sbias);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
@@ -162,21 +166,24 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
       uint32_t v[2][16];
-      tc_ld16(taddr, v[0]);
+      constexpr int kChunks = 4 / kColSplit;
+      const int c_first = cpart * kChunks;
+      tc_ld16(taddr + (uint32_t)(c_first * 16), v[0]);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
+      for (int ci = 0; ci < kChunks; ci++) {
+        const int c4 = c_first + ci;
         tc_ld_wait();
-        if (c4 < 3) tc_ld16(taddr + (uint32_t)((c4 + 1) * 16), v[(c4 + 1) & 1]);
+        if (ci < kChunks - 1) tc_ld16(taddr + (uint32_t)((c4 + 1) * 16), v[(ci + 1) & 1]);
         uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
         if (inside) {
           float f[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
             const float4 b = lds128f(sbias_s + (uint32_t)((c4 * 16 + j4 * 4) * 4));
-            f[4 * j4] = __uint_as_float(v[c4 & 1][4 * j4]) + b.x;
-            f[4 * j4 + 1] = __uint_as_float(v[c4 & 1][4 * j4 + 1]) + b.y;
-            f[4 * j4 + 2] = __uint_as_float(v[c4 & 1][4 * j4 + 2]) + b.z;
-            f[4 * j4 + 3] = __uint_as_float(v[c4 & 1][4 * j4 + 3]) + b.w;
+            f[4 * j4] = __uint_as_float(v[ci & 1][4 * j4]) + b.x;
+            f[4 * j4 + 1] = __uint_as_float(v[ci & 1][4 * j4 + 1]) + b.y;
+            f[4 * j4 + 2] = __uint_as_float(v[ci & 1][4 * j4 + 2]) + b.z;
+            f[4 * j4 + 3] = __uint_as_float(v[ci & 1][4 * j4 + 3]) + b.w;
           }
           __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
           const __half2 z = __float2half2_rn(0.0f);
@@ -195,8 +202,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       // ---- 3x3 stride-2 max over the staging tile: item = (pooled pixel, 8-channel chunk) ----
 #pragma unroll
-      for (int rnd = 0; rnd < 2; rnd++) {
-        const int item = et + rnd * 256;
+      for (int rnd = 0; rnd < (kPool * kPool * 8 + 32 * kEpiWarps - 1) / (32 * kEpiWarps); rnd++) {
+        const int item = et + rnd * 32 * kEpiWarps;
         if (item < kPool * kPool * 8) {
           const int c = item & 7, pp = item >> 3, pi = pp / kPool, pj = pp - pi * kPool;
           const int ph = ph0 + pi, pw = pw0 + pj;

@@ -84,8 +84,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (.release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive (~2000 cycles
+// per call, measured with the in-kernel wait profile of bottleneck.cu).  What the waiter consumes is ordered by the
+// tcgen05 / async-proxy fences the callers execute before arriving.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // cta_group::2 TMA loads: destination in the executing CTA, completion counted on a barrier that may live in the peer
 __device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {

@@ -180,6 +180,7 @@ class Model:
         self.fused_candidates = os.environ.get("ODTK_FUSED_CANDIDATES", "1") != "0"
         self.fused_stem = os.environ.get("ODTK_FUSED_STEM", "1") != "0"
         self.merged_heads = os.environ.get("ODTK_MERGED_HEADS", "1") != "0"
+        self.fused_bneck = os.environ.get("ODTK_FUSED_BNECK", "1") != "0"
         self._atlas = {}
         self._fused = {}
         self._head_streams = None
@@ -337,10 +338,19 @@ class Model:
         for blk in P["blocks"]:
             identity = x if blk["down"] is None else blk["down"](x)
             cs = blk["convs"]
-            out = x
-            for c in cs[:-1]:
-                out = c(out, relu=True)
-            x = cs[-1](out, relu=True, residual=identity)
+            if (self.fused_bneck and len(cs) == 3 and cs[1].stride == 1 and cs[1].groups == 1 and cs[1].ks == 3 and
+                    cs[1].cin in (64, 128) and cs[1].cout == cs[1].cin and cs[2].cin == cs[1].cin and cs[2].cout % 128 == 0 and
+                    cs[2].cout <= 512):
+                # conv2 (3x3) + conv3 (1x1) + identity + ReLU in one kernel: the 3x3's output never leaves the SM
+                out = cs[0](x, relu=True)
+                px = out.shape[0] * out.shape[1] * out.shape[2]
+                engine.STATS["conv_flops"] += 2 * px * cs[1].cin * (9 * cs[1].cin + cs[2].cout)
+                x = engine.bottleneck_tail(out, cs[1].w, cs[1].b, cs[2].w, cs[2].b, identity, relu=True)
+            else:
+                out = x
+                for c in cs[:-1]:
+                    out = c(out, relu=True)
+                x = cs[-1](out, relu=True, residual=identity)
             if blk["last"]:
                 outs[blk["level"]] = x
         c3, c4, c5 = outs[3], outs[4], outs[5]

@@ -347,3 +347,28 @@ def test_grouped_conv3x3_resnext(n, h, w, c, groups, stride):
     assert plan["bn"] == 64 and plan["num_n_tiles"] == c // 64, plan
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=stride, padding=1, groups=groups)
     _close16(y, F.relu(ref))
+
+
+@pytest.mark.parametrize("n,h,w,c1", [(2, 24, 48, 64), (1, 9, 17, 64), (3, 8, 16, 128), (1, 20, 40, 128), (2, 13, 21, 64),
+                                      (4, 200, 320, 64), (2, 100, 160, 128)])
+def test_bottleneck_tail_fused_matches_torch_and_two_kernel_route(n, h, w, c1):
+    """conv2 (3x3) + bn + relu + conv3 (1x1) + bn + identity + relu in ONE kernel (bottleneck.cu): against torch fp32 with
+    the intermediate rounded to fp16 (what the two-kernel route stores), and against the two-kernel route itself
+    (conv.cu halo 3x3, then 1x1 + residual).  Ragged tiles, an odd tile count (padding tile of the last CTA pair) and
+    many tiles per CTA are covered."""
+    c2 = 4 * c1
+    g = torch.Generator().manual_seed(n * 7 + h + w + c1)
+    x = _rand((n, h, w, c1), g)
+    w2, b2 = _rand((c1, c1, 3, 3), g, 0.04), torch.randn(c1, generator=g) * 0.5
+    w3, b3 = _rand((c2, c1, 1, 1), g, 0.08), torch.randn(c2, generator=g) * 0.5
+    res = _rand((n, h, w, c2), g)
+    w2p, w3p = engine.pack_weight(w2.float()).to(DEV), engine.pack_weight(w3.float()).to(DEV)
+    xd, rd, b2d, b3d = x.to(DEV), res.to(DEV), b2.to(DEV), b3.to(DEV)
+    y = engine.bottleneck_tail(xd, w2p, b2d, w3p, b3d, rd, relu=True)
+    torch.cuda.synchronize()
+    mid = _ref_conv(x, w2, b2, 3, relu=True).permute(0, 2, 3, 1).to(torch.float16)          # fp16, as stored between the kernels
+    _close16(y, _ref_conv(mid, w3, b3, 1, relu=True, residual=res))
+    mid_d = engine.conv2d(xd, w2p, b2d, c1, 3, relu=True, bias_op=engine.pack_bias(b2d))
+    y2 = engine.conv2d(mid_d, w3p, b3d, c2, 1, relu=True, residual=rd, bias_op=engine.pack_bias(b3d))
+    err = (y.float() - y2.float()).abs().max().item()
+    assert err <= 2e-3 * y2.float().abs().max().item() + 1e-3, err

@@ -219,10 +219,13 @@ def test_heads_match_fp16_emulating_oracle(backbone, shape, rotated):
     m = Model(backbone, classes=5, rotated_bbox=rotated).load_state_dict(sd).cuda()
     cls, box = m.forward_heads(x.to(DEV), sigmoid=False)
     rc, rb = model_ref.forward_heads(sd, backbone, x, sigmoid=False, fp16=True)
+    # both sides round every activation to fp16; a different fp32 summation order flips the last fp16 bit of a few of
+    # them per layer, which random-walks through the depth: 2e-3 through ~60 layers, 3e-3 through the 100+-layer backbones
+    bar = 3e-3 if backbone in ("ResNet152FPN", "ResNeXt101_32x8dFPN") else 2e-3
     for i in range(5):
         assert tuple(cls[i].shape) == tuple(rc[i].shape) and tuple(box[i].shape) == tuple(rb[i].shape)
-        assert _rel_err(cls[i].cpu(), rc[i]) < 2e-3, ("cls", i, _rel_err(cls[i].cpu(), rc[i]))
-        assert _rel_err(box[i].cpu(), rb[i]) < 2e-3, ("box", i, _rel_err(box[i].cpu(), rb[i]))
+        assert _rel_err(cls[i].cpu(), rc[i]) < bar, ("cls", i, _rel_err(cls[i].cpu(), rc[i]))
+        assert _rel_err(box[i].cpu(), rb[i]) < bar, ("box", i, _rel_err(box[i].cpu(), rb[i]))
 
 
 @pytest.mark.parametrize("backbone,shape", [("ResNet18FPN", (2, 3, 256, 256)), ("ResNet50FPN", (1, 3, 256, 384))])

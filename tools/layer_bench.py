@@ -33,7 +33,7 @@ def main():
     tf, bw = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"], peaks["hbm_gbs"]
 
     calls = []
-    names = ["conv2d", "stem_conv", "stem_conv_padded", "maxpool3x3s2", "lower_conv", "relu", "pad_input", "stem_pool_padded"]
+    names = ["conv2d", "stem_conv", "stem_conv_padded", "maxpool3x3s2", "lower_conv", "relu", "pad_input", "stem_pool_padded", "bottleneck_tail"]
     orig = {n: getattr(engine, n) for n in names if hasattr(engine, n)}
 
     def wrap(name):

@@ -9,7 +9,7 @@ import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL_KIND = [("conv_gemm_kernel", ("conv1x1", "conv3x3", "stem7x7")), ("lower", ("lower_conv",)), ("maxpool", ("maxpool",)),
+KERNEL_KIND = [("conv_gemm_kernel", ("conv1x1", "conv3x3", "stem7x7")), ("bottleneck_tail_kernel", ("bneck_tail",)), ("stem_pool_kernel", ("stem_pool",)), ("lower", ("lower_conv",)), ("maxpool", ("maxpool",)),
                ("pad_input", ("pad_input",)), ("preprocess", ("preprocess_u8",))]
 
 
