@@ -11,10 +11,11 @@
 //             Accumulator acc1[2] (C1 <= 128 TMEM columns each).
 //   ep1       epilogue warps: acc1 + b2 -> ReLU -> fp16 -> shared memory, written directly in the K-major SWIZZLE_128B
 //             layout of a UMMA A operand ("y1").
-//   GEMM2     1x1: for every 128-channel output tile n2: acc2[n2 & 1] = y1 * W3[n2]^T, then the identity is added ON THE
-//             TENSOR CORE: acc2[:, 64 j ..] += R_j * I^T with R_j the [128 px x 64 ch] identity chunk (A operand, loaded by
-//             TMA straight from the NHWC tensor) and I the 64 x 64 identity matrix.
-//   ep2       acc2 + b3 -> ReLU -> fp16 -> 128B-swizzled slab -> cp.async.bulk.tensor store (4-D box, edges clipped).
+//   GEMM2     1x1: for every 128-channel output tile n2: acc2[n2 & 1] = y1 * W3[n2]^T.
+//   ep2       the identity chunks [128 px x 64 ch] arrive by TMA (4-D box straight from the NHWC tensor, 128B-swizzled rows
+//             = pixels) in a ring of 16 KB slots; each epilogue thread adds ITS pixel's 128 bytes to acc2 + b3, applies
+//             ReLU and writes the fp16 result back IN PLACE; the slot's 4 KB quarter of the warp is then the source of a
+//             cp.async.bulk.tensor store (4-D box, edges clipped by the TMA unit).  No staging slabs, no extra pass.
 //
 //   warp 0 TMA producer (patches + weights), warp 3 TMA producer of the identity chunks (the HBM stream that bounds the
 //   kernel: its own ring, never blocked behind a weight slot), warp 1 MMA issuer (leader CTA of the pair), warp 2 TMEM
@@ -40,11 +41,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kNPatch = 2;
 constexpr int kRSlot = 16384;                  // identity chunk: 128 pixels x 64 channels
-constexpr int kMaxRSlots = 4;
+constexpr int kMaxRSlots = 6;
 constexpr int kWSlot = 8192;                   // streamed weight block: this CTA's 64 rows x 64 K
-constexpr int kMaxWSlots = 5;
-constexpr int kSlabBytes = 32 * 128;
-constexpr int kIdentBytes = 32 * 128;          // this CTA's 32 rows of the 64 x 64 identity
+constexpr int kMaxWSlots = 8;
 constexpr int kBiasBytes = 2560;               // b2 (<= 128 fp32) + b3 (<= 512 fp32)
 constexpr int kBarBytes = 512;
 constexpr int kTmemCols = 512;
@@ -72,7 +71,7 @@ struct BtBars {
   uint64_t rfull[kMaxRSlots], rempty[kMaxRSlots];
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t acc2_full[2], acc2_empty[2];
-  uint64_t y1_full[2], y1_empty[2], ident_full, wres_full;
+  uint64_t y1_full[2], y1_empty[2], wres_full;
   uint32_t tmem_base;
 };
 static_assert(sizeof(BtBars) <= kBarBytes, "barrier block too small");
@@ -102,11 +101,11 @@ __device__ __forceinline__ uint64_t bt_desc_halo(uint32_t saddr, uint32_t sbo) {
 __global__ void __launch_bounds__(kThreads, 1)
 bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmR,
-                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmI,
+                       const __grid_constant__ CUtensorMap tmY,
                        const __grid_constant__ BtParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // layout (every region 1024-aligned): patches | weights (resident, or ring) | identity ring | y1 | ident | slabs | bias | barriers
+  // layout (every region 1024-aligned): patches | weights (resident, or ring) | identity ring | y1 | bias | barriers
   const int kc1 = p.C1 >> 6;                         // 64-channel chunks of the 3x3's input == of y1
   const int n2tiles = p.C2 >> 7;
   const uint32_t w2_block = (uint32_t)(p.C1 >> 1) * 128u;    // this CTA's half of the rows of one W2 block (tap, chunk)
@@ -116,9 +115,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot : (uint32_t)p.nw * kWSlot;
   unsigned char *sres = sw + w_bytes;
   unsigned char *sy1 = sres + p.nr * kRSlot;
-  unsigned char *sident = sy1 + 2 * kc1 * 16384;    // y1 is double-buffered: ep1(t+1) does not wait for GEMM2(t)
-  unsigned char *sslab = sident + kIdentBytes;
-  float *sbias = reinterpret_cast<float *>(sslab + kEpiWarps * kSlabBytes);
+  float *sbias = reinterpret_cast<float *>(sy1 + 2 * kc1 * 16384);    // y1 is double-buffered: ep1(t+1) does not wait for GEMM2(t)
   BtBars *bars = reinterpret_cast<BtBars *>(reinterpret_cast<unsigned char *>(sbias) + kBiasBytes);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
@@ -134,13 +131,13 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kNPatch; s++) { mbar_init(&bars->pfull[s], 1); mbar_init(&bars->pempty[s], 1); }
     for (int s = 0; s < kMaxWSlots; s++) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
-    for (int s = 0; s < kMaxRSlots; s++) { mbar_init(&bars->rfull[s], 1); mbar_init(&bars->rempty[s], 1); }
+    for (int s = 0; s < kMaxRSlots; s++) { mbar_init(&bars->rfull[s], 1); mbar_init(&bars->rempty[s], 4); }   // a slot is consumed by the 4 epilogue warps of one column half
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 2 * kEpiWarps);   // one arrival per epilogue warp of the pair
       mbar_init(&bars->acc2_full[b], 1); mbar_init(&bars->acc2_empty[b], 2 * kEpiWarps);
       mbar_init(&bars->y1_full[b], 2 * kEpiWarps); mbar_init(&bars->y1_empty[b], 1);
     }
-    mbar_init(&bars->ident_full, 1); mbar_init(&bars->wres_full, 1);
+    mbar_init(&bars->wres_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -173,10 +170,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // ============================ TMA producer: patches + weights ============================
     int ws = 0, pb = 0;
     uint32_t wph = 0, pphase = 0;
-    if (elect_one()) {
-      if (crank == 0) mbar_arrive_expect_tx(&bars->ident_full, 2u * kIdentBytes);
-      tma2_load_2d(sident, &tmI, mapa_rank(smem_u32(&bars->ident_full), 0), 0, 32 * crank);
-    }
     if (p.w_resident && elect_one()) {
       const uint32_t lbar = mapa_rank(smem_u32(&bars->wres_full), 0);
       if (crank == 0) mbar_arrive_expect_tx(&bars->wres_full, 2u * w_bytes);
@@ -238,9 +231,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       tile_of(pair, img, h0, w0);
       for (int c = 0; c < 2 * n2tiles; c++) {
         BT_WAIT(10, &bars->rempty[rs], rph ^ 1u);
-        if (elect_one()) {
-          if (crank == 0) mbar_arrive_expect_tx(&bars->rfull[rs], 2u * (uint32_t)kRSlot);
-          tma2_load_4d(sres + rs * kRSlot, &tmR, mapa_rank(smem_u32(&bars->rfull[rs]), 0), c * 64, h0, w0, img);
+        if (elect_one()) {                            // this CTA's own barrier: the two identity streams of a pair are independent
+          mbar_arrive_expect_tx(&bars->rfull[rs], (uint32_t)kRSlot);
+          tma_load_4d(sres + rs * kRSlot, &tmR, &bars->rfull[rs], c * 64, h0, w0, img);
         }
         if (++rs == p.nr) { rs = 0; rph ^= 1u; }
       }
@@ -251,13 +244,11 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (crank == 0) {
       const uint32_t idesc1 = (1u << 4) | ((uint32_t)(p.C1 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      const uint32_t idesc_r = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      const uint32_t w_s = smem_u32(sw), res_s = smem_u32(sres), patch_s = smem_u32(spatch), y1_s = smem_u32(sy1), ident_s = smem_u32(sident);
+      const uint32_t w_s = smem_u32(sw), patch_s = smem_u32(spatch), y1_s = smem_u32(sy1);
       const uint32_t sbo = (uint32_t)p.ppitch * 128u;
-      int ws = 0, rs = 0, pb = 0;
-      uint32_t wph = 0, rph = 0, pphase = 0;
+      int ws = 0, pb = 0;
+      uint32_t wph = 0, pphase = 0;
       int it1 = 0, it2 = 0, u2 = 0;                  // G1 / G2 invocation counters, acc2 use counter
-      mbar_wait(&bars->ident_full, 0);
       if (p.w_resident) mbar_wait(&bars->wres_full, 0);
       tc_fence_after();
       auto issue_g1 = [&]() {
@@ -319,18 +310,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
             if (!p.w_resident) { if (++ws == p.nw) { ws = 0; wph ^= 1u; } }
           }
-          for (int j = 0; j < 2; j++) {
-            BT_WAIT(5, &bars->rfull[rs], rph);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = make_desc_kmajor(res_s + (uint32_t)(rs * kRSlot), 128);
-              const uint64_t db = make_desc_kmajor(ident_s, 128);
-#pragma unroll
-              for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_d + (uint32_t)(64 * j), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_r, 1u);
-              tc_commit2_mc(&bars->rempty[rs], (uint16_t)3);
-            }
-            if (++rs == p.nr) { rs = 0; rph ^= 1u; }
-          }
           if (elect_one()) tc_commit2_mc(&bars->acc2_full[buf], (uint16_t)3);
         }
         if (elect_one()) tc_commit2_mc(&bars->y1_empty[yb], (uint16_t)3);
@@ -348,7 +327,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // ===================================== epilogue ==========================================
     const int q = warp & 3, sg = (warp - 4) >> 2;
     const int row = q * 32 + lane;                   // accumulator row == pixel (row % 8, row / 8) of the tile
-    const uint32_t slab_s = smem_u32(sslab + (warp - 4) * kSlabBytes);
     const uint32_t y1_s = smem_u32(sy1), sb_s = smem_u32(sbias);
     const uint32_t lbar_acc1e0 = mapa_rank(smem_u32(&bars->acc1_empty[0]), 0), lbar_acc1e1 = mapa_rank(smem_u32(&bars->acc1_empty[1]), 0);
     const uint32_t lbar_acc2e0 = mapa_rank(smem_u32(&bars->acc2_empty[0]), 0), lbar_acc2e1 = mapa_rank(smem_u32(&bars->acc2_empty[1]), 0);
@@ -403,25 +381,37 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
     };
     int u2 = 0;
-    // ---- ep2: per 128-channel output tile: acc2 (+ identity, added by the tensor core) + b3 -> ReLU -> fp16 -> store ----
+    int held = -1;                                   // identity slot this warp's last bulk store still reads from
+    const uint32_t res_s = smem_u32(sres);
+    // ---- ep2: per 128-channel output tile: acc2 + b3 + identity -> ReLU -> fp16, in place in the identity slot -> store ----
     auto ep2 = [&](int pair) {
       int img, h0, w0;
       const bool real = tile_of(pair, img, h0, w0);
       for (int n2 = 0; n2 < n2tiles; n2++, u2++) {
         const int buf = u2 & 1;
-        BT_WAIT(14, &bars->acc2_full[buf], (uint32_t)(u2 >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(buf * 128 + sg * 64);
+        const int cidx = 2 * u2 + sg;                // running index of the identity chunk this warp consumes
+        const int slot = cidx % p.nr;
         BT_T0(ta_);
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the slab
-        __syncwarp();
+        if (held >= 0) {                             // hand the previous slot back once its store has read it
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&bars->rempty[held]);
+          }
+          held = -1;
+        }
         BT_ADD(17, ta_);
+        BT_WAIT(14, &bars->acc2_full[buf], (uint32_t)(u2 >> 1) & 1u);
+        BT_WAIT(15, &bars->rfull[slot], (uint32_t)(cidx / p.nr) & 1u);
+        tc_fence_after();
         BT_T0(tb_);
-        const uint32_t srow = slab_s + (uint32_t)(lane * 128);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(buf * 128 + sg * 64);
+        const uint32_t srow = res_s + (uint32_t)(slot * kRSlot + row * 128);   // this thread's pixel: 64 channels, 128B-swizzled
         uint32_t v[2][16];
         tc_ld16(taddr, v[0]);
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
+          const uint32_t a0 = srow + (uint32_t)(((2 * cc) ^ (row & 7)) << 4), a1 = srow + (uint32_t)(((2 * cc + 1) ^ (row & 7)) << 4);
+          const uint4 r0 = lds128(a0), r1 = lds128(a1);
           tc_ld_wait();
           if (cc < 3) tc_ld16(taddr + (uint32_t)((cc + 1) * 16), v[(cc + 1) & 1]);
           const int col0 = n2 * 128 + sg * 64 + cc * 16;
@@ -433,6 +423,12 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             f[4 * j4 + 1] = __uint_as_float(v[cc & 1][4 * j4 + 1]) + b.y;
             f[4 * j4 + 2] = __uint_as_float(v[cc & 1][4 * j4 + 2]) + b.z;
             f[4 * j4 + 3] = __uint_as_float(v[cc & 1][4 * j4 + 3]) + b.w;
+          }
+          const __half2 *x0 = reinterpret_cast<const __half2 *>(&r0), *x1 = reinterpret_cast<const __half2 *>(&r1);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 a = __half22float2(x0[j]), b = __half22float2(x1[j]);
+            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
           }
           uint4 o0, o1;
           __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
@@ -446,8 +442,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; j++) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
           }
-          sts128(srow + (uint32_t)(((2 * cc) ^ (lane & 7)) << 4), o0);
-          sts128(srow + (uint32_t)(((2 * cc + 1) ^ (lane & 7)) << 4), o1);
+          sts128(a0, o0);
+          sts128(a1, o1);
         }
         BT_ADD(18, tb_);
         BT_T0(tc_);
@@ -457,15 +453,17 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         BT_ADD(19, tc_);
         BT_T0(td_);
         if (lane == 0) {
-          mbar_arrive_remote(buf ? lbar_acc2e1 : lbar_acc2e0);   // the accumulator is in the slab: hand it back (one arrival per warp)
+          mbar_arrive_remote(buf ? lbar_acc2e1 : lbar_acc2e0);   // the accumulator has been read: hand it back (one arrival per warp)
           if (real) {
-            // 32 pixels = 8 rows x 4 columns of the tile; pixels outside the image are clipped by the TMA unit
+            // 32 pixels = 8 rows x 4 columns of the tile = this warp's 4 KB quarter of the slot; pixels outside the image
+            // are clipped by the TMA unit
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(&tmY), "r"(slab_s), "r"(n2 * 128 + sg * 64), "r"(h0), "r"(w0 + 4 * q), "r"(img)
+                         ::"l"(&tmY), "r"(res_s + (uint32_t)(slot * kRSlot + q * 4096)), "r"(n2 * 128 + sg * 64), "r"(h0), "r"(w0 + 4 * q), "r"(img)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        held = slot;
         __syncwarp();
         BT_ADD(20, td_);
       }
@@ -477,6 +475,10 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int pair = c_first; pair < npairs; pair += c_step) {
       if (pair + c_step < npairs) ep1(it++);
       ep2(pair);
+    }
+    if (held >= 0 && lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_arrive(&bars->rempty[held]);
     }
     if (warp == 4) { BT_TOTAL_END(16); }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -514,12 +516,7 @@ bool bt_encode(CUtensorMap *m, const void *base, int rank, const uint64_t *dims,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-__device__ __half g_bt_ident[64 * 64];
-__global__ void bt_init_ident_kernel() {
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) g_bt_ident[i] = __float2half_rn((i >> 6) == (i & 63) ? 1.0f : 0.0f);
-}
-
-struct BtDevice { bool ready; void *ident; };
+struct BtDevice { bool ready; };
 BtDevice g_bt_dev[64];
 std::mutex g_bt_mu;
 
@@ -530,13 +527,6 @@ const BtDevice *bt_device(cudaStream_t stream) {
   BtDevice &d = g_bt_dev[dev];
   if (d.ready) return &d;
   if (cudaFuncSetAttribute(bottleneck_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) return nullptr;
-  if (cudaGetSymbolAddress(&d.ident, g_bt_ident) != cudaSuccess) return nullptr;
-  bt_init_ident_kernel<<<1, 256, 0, stream>>>();
-  if (cudaGetLastError() != cudaSuccess) return nullptr;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
-    if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
-  }
   d.ready = true;
   return &d;
 }
@@ -571,7 +561,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   static int pitch = -1, nr_cap = -1;
   if (pitch < 0) {
     const char *e = getenv("ODTK_BNECK_PITCH"); pitch = (e && atoi(e) == 16) ? 16 : 10;
-    const char *r = getenv("ODTK_BNECK_NR"); nr_cap = r ? atoi(r) : kMaxRSlots;
+    const char *r = getenv("ODTK_BNECK_NR"); nr_cap = r ? atoi(r) : 4;   // measured (B200, layer_bench): 4 slots 388 / 262 us (C1 = 64 / 128), 6 slots 418 / 300
     if (nr_cap < 2 || nr_cap > kMaxRSlots) nr_cap = kMaxRSlots;
   }
   p.ppitch = pitch;
@@ -580,9 +570,11 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   const int kc1 = d->c1 / 64, n2tiles = d->c2 / 128;
   const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot;
   if (p.w_resident && w_resident_bytes > 60 * 1024) p.w_resident = 0;
-  const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kIdentBytes + kEpiWarps * kSlabBytes + kBiasBytes + kBarBytes;
+  const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kBiasBytes + kBarBytes;
   // shared-memory budget: identity ring as deep as it gets (it carries the HBM stream), then the weight ring
-  p.nw = p.w_resident ? 0 : 4;
+  static int nw_min = -1;
+  if (nw_min < 0) { const char *e = getenv("ODTK_BNECK_NW"); nw_min = e ? atoi(e) : 4; if (nw_min < 2 || nw_min > kMaxWSlots) nw_min = 4; }
+  p.nw = p.w_resident ? 0 : nw_min;
   int left = kSmemMax - fixed - (p.w_resident ? w_resident_bytes : p.nw * kWSlot);
   p.nr = left / kRSlot;
   if (p.nr > nr_cap) p.nr = nr_cap;
@@ -593,7 +585,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   p.relu = d->relu;
   p.b2 = d->b2; p.b3 = d->b3;
   const uint64_t C1 = (uint64_t)d->c1, C2 = (uint64_t)d->c2, H = (uint64_t)d->h, W = (uint64_t)d->width, N = (uint64_t)d->n;
-  CUtensorMap tmX, tmW2, tmW3, tmR, tmY, tmI;
+  CUtensorMap tmX, tmW2, tmW3, tmR, tmY;
   {
     uint64_t dims[4] = {C1, H, W, N}, str[3] = {W * C1 * 2, C1 * 2, H * W * C1 * 2};
     uint32_t box[4] = {64, (uint32_t)p.ppitch, 18, 1};
@@ -614,11 +606,6 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
     uint32_t boxR[4] = {64, 8, 16, 1}, boxY[4] = {64, 8, 4, 1};
     if (!bt_encode(&tmR, d->residual, 4, dims, str, boxR) || !bt_encode(&tmY, d->y, 4, dims, str, boxY)) return ODTK_E_CUDA;
   }
-  {
-    uint64_t dims[2] = {64, 64}, str[1] = {128};
-    uint32_t box[2] = {64, 32};
-    if (!bt_encode(&tmI, ds->ident, 2, dims, str, box)) return ODTK_E_CUDA;
-  }
   const int sms = odtk_sm_count();
   const int npairs = (p.total_tiles + 1) / 2;
   int clusters = sms / 2;
@@ -635,7 +622,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   cfg.numAttrs = 1;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmI, p);
+    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -5,9 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from retinanet_examples_b200 import engine, _lib
-NAMES = {0: "mma acc1_empty", 1: "mma pfull", 2: "mma wfull", 3: "mma y1_full", 4: "mma acc2_empty", 5: "mma rfull", 6: "mma TOTAL",
+NAMES = {0: "mma acc1_empty", 1: "mma pfull", 2: "mma wfull", 3: "mma y1_full", 4: "mma acc2_empty", 6: "mma TOTAL",
          7: "prodA pempty", 8: "prodA wempty", 9: "prodA TOTAL", 10: "prodR rempty", 11: "prodR TOTAL",
-         12: "epi acc1_full (sum of 8 warps)", 13: "epi y1_empty (8 warps)", 14: "epi acc2_full (8 warps)", 16: "epi TOTAL (warp 4)", 17: "epi2 wait_group.read (warp 4)", 18: "epi2 tmem ld + math + sts (warp 4)", 19: "epi2 fences + syncwarp (warp 4)", 20: "epi2 arrive + store issue (warp 4)"}
+         12: "epi acc1_full (sum of 8 warps)", 13: "epi y1_empty (8 warps)", 14: "epi acc2_full (8 warps)", 15: "epi rfull (8 warps)", 16: "epi TOTAL (warp 4)", 17: "epi2 wait_group.read (warp 4)", 18: "epi2 tmem ld + math + sts (warp 4)", 19: "epi2 fences + syncwarp (warp 4)", 20: "epi2 arrive + store issue (warp 4)"}
 lib = _lib.lib()
 g = torch.Generator().manual_seed(0)
 for (n, h, w, c1) in ((32, 200, 320, 64), (32, 100, 160, 128)):
