@@ -229,6 +229,12 @@ typedef struct {
 int odtk_conv_last_plan(odtk_conv_plan_t *out);
 /* Encoded tensor maps are cached per (base pointer, geometry); hit / miss counters of the process.         */
 int odtk_conv_map_cache_stats(long long *hits, long long *misses);
+/* Launch budget: the persistent kernels of this library launched by the calling process after this call use at most `sms`
+ * CTAs (0 = the whole device).  Two streams with complementary budgets run side by side on disjoint SMs: the tensor-bound
+ * head towers of one half batch next to the HBM-bound backbone layers of the other (Model.forward, pipelined mode).  A CUDA
+ * graph keeps the grids it was captured with.                                                                          */
+int odtk_set_sm_budget(int sms);
+
 /* Tail of a stride-1 ResNet bottleneck block in ONE kernel (torchvision Bottleneck.forward behind
  * odtk/backbones/resnet.py:24-39; the reference runs it as two cuDNN convolutions + an elementwise add):
  *     y = relu( conv1x1( relu( conv3x3(x, w2) + b2 ), w3 ) + b3 + residual )
@@ -241,6 +247,10 @@ typedef struct {
   const float *b2, *b3;
   void *y;
   int n, h, width, c1, c2, relu;
+  /* first block of layer1 (its identity is a 1x1 projection of the 64-channel block input, torchvision `downsample`): when
+   * xproj != NULL the kernel computes identity = xproj [n, h, width, 64] x wproj [c2, 64]^T itself on the tensor core
+   * (residual is ignored, b3 must already include the projection's bias); c1 must be 64.                          */
+  const void *xproj, *wproj;
 } odtk_bneck_t;
 int odtk_bottleneck_tail(const odtk_bneck_t *desc, odtk_stream_t stream);
 /* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */

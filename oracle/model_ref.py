@@ -76,7 +76,11 @@ def features(sd, backbone, x, fp16=False):
                 out = _q(F.relu(_cb(sd, p + "conv1", p + "bn1", x, stride, 1, fp16)), fp16)
                 out = _cb(sd, p + "conv2", p + "bn2", out, 1, 1, fp16)
             if (p + "downsample.0.weight") in sd:
-                identity = _q(_cb(sd, p + "downsample.0", p + "downsample.1", x, stride, 0, fp16), fp16)
+                identity = _cb(sd, p + "downsample.0", p + "downsample.1", x, stride, 0, fp16)
+                # the product path computes the stride-1 projection of layer1's first bottleneck block inside the fused
+                # block kernel (bottleneck.cu) and adds it in fp32; every other projected identity is stored in fp16
+                if not (block == "bottleneck" and stride == 1 and backbone not in GROUPS):
+                    identity = _q(identity, fp16)
             x = _q(F.relu(out + identity), fp16)
         if li >= 1:
             outs.append(x)

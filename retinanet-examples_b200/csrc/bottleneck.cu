@@ -72,6 +72,7 @@ struct BtBars {
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t acc2_full[2], acc2_empty[2];
   uint64_t y1_full[2], y1_empty[2], wres_full;
+  uint64_t xfull[2], xempty[2];          // projection mode: the block input tile (A operand of the identity GEMM)
   uint32_t tmem_base;
 };
 static_assert(sizeof(BtBars) <= kBarBytes, "barrier block too small");
@@ -84,6 +85,7 @@ struct BtParams {
   int w_resident;        // C1 == 64: W2 / W3 halves stay in shared memory (52 KB); else they stream through the weight ring
   int nw, nr;            // weight / identity ring depths
   int relu;
+  int proj;              // identity = 1x1 projection of a 64-channel block input, computed here (first block of layer1)
   const float *b2, *b3;
 };
 
@@ -101,7 +103,7 @@ __device__ __forceinline__ uint64_t bt_desc_halo(uint32_t saddr, uint32_t sbo) {
 __global__ void __launch_bounds__(kThreads, 1)
 bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmR,
-                       const __grid_constant__ CUtensorMap tmY,
+                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
                        const __grid_constant__ BtParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -112,9 +114,11 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const int nb1 = 9 * kc1;                           // W2 blocks per tile, linear index b = chunk * 9 + tap
   unsigned char *spatch = smem;
   unsigned char *sw = spatch + kNPatch * p.patch_slot;
-  const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot : (uint32_t)p.nw * kWSlot;
+  const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot + (p.proj ? (uint32_t)n2tiles * kWSlot : 0u)
+                                        : (uint32_t)p.nw * kWSlot;
   unsigned char *sres = sw + w_bytes;
-  unsigned char *sy1 = sres + p.nr * kRSlot;
+  unsigned char *sx = sres + p.nr * kRSlot;          // projection mode: 2 slots for the block-input tile
+  unsigned char *sy1 = sx + (p.proj ? 2 * kRSlot : 0);
   float *sbias = reinterpret_cast<float *>(sy1 + 2 * kc1 * 16384);    // y1 is double-buffered: ep1(t+1) does not wait for GEMM2(t)
   BtBars *bars = reinterpret_cast<BtBars *>(reinterpret_cast<unsigned char *>(sbias) + kBiasBytes);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -138,6 +142,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       mbar_init(&bars->y1_full[b], 2 * kEpiWarps); mbar_init(&bars->y1_empty[b], 1);
     }
     mbar_init(&bars->wres_full, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&bars->xfull[s], 1); mbar_init(&bars->xempty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -180,6 +185,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       for (int n2 = 0; n2 < n2tiles; n2++)
         for (int kc = 0; kc < kc1; kc++)
           tma2_load_2d(sw + nb1 * w2_block + (n2 * kc1 + kc) * kWSlot, &tmW3, lbar, kc * 64, n2 * 128 + crank * 64);
+      if (p.proj)
+        for (int n2 = 0; n2 < n2tiles; n2++)
+          tma2_load_2d(sw + nb1 * w2_block + (n2tiles * kc1 + n2) * kWSlot, &tmWd, lbar, 0, n2 * 128 + crank * 64);
     }
     auto produce_g1 = [&](int pair) {
       int img, h0, w0;
@@ -226,9 +234,20 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     int rs = 0;
     uint32_t rph = 0;
     BT_TOTAL_BEGIN();
+    int xs = 0;
+    uint32_t xph = 0;
     for (int pair = c_first; pair < npairs; pair += c_step) {
       int img, h0, w0;
       tile_of(pair, img, h0, w0);
+      if (p.proj) {                                  // one 64-channel tile of the block input per tile (pair protocol: the MMA reads both CTAs')
+        mbar_wait(&bars->xempty[xs], xph ^ 1u);
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&bars->xfull[xs], 2u * (uint32_t)kRSlot);
+          tma2_load_4d(sx + xs * kRSlot, &tmR, mapa_rank(smem_u32(&bars->xfull[xs]), 0), 0, h0, w0, img);
+        }
+        if (++xs == 2) { xs = 0; xph ^= 1u; }
+        continue;
+      }
       for (int c = 0; c < 2 * n2tiles; c++) {
         BT_WAIT(10, &bars->rempty[rs], rph ^ 1u);
         if (elect_one()) {                            // this CTA's own barrier: the two identity streams of a pair are independent
@@ -249,6 +268,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       int ws = 0, pb = 0;
       uint32_t wph = 0, pphase = 0;
       int it1 = 0, it2 = 0, u2 = 0;                  // G1 / G2 invocation counters, acc2 use counter
+      int xs = 0;
+      uint32_t xph = 0;
+      const uint32_t x_s = smem_u32(sx);
       if (p.w_resident) mbar_wait(&bars->wres_full, 0);
       tc_fence_after();
       auto issue_g1 = [&]() {
@@ -287,6 +309,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       auto issue_g2 = [&]() {
         const int yb = it2 & 1;
         BT_WAIT(3, &bars->y1_full[yb], (uint32_t)(it2 >> 1) & 1u);
+        if (p.proj) mbar_wait(&bars->xfull[xs], xph);
         tc_fence_after();
         for (int n2 = 0; n2 < n2tiles; n2++, u2++) {
           const int buf = u2 & 1;
@@ -310,9 +333,19 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
             if (!p.w_resident) { if (++ws == p.nw) { ws = 0; wph ^= 1u; } }
           }
+          if (p.proj && elect_one()) {               // + identity: block-input tile x Wd[n2]^T into the same accumulator
+            const uint64_t da = make_desc_kmajor(x_s + (uint32_t)(xs * kRSlot), 128);
+            const uint64_t db = make_desc_kmajor(w_s + (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1 + n2) * kWSlot, 128);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, 1u);
+          }
           if (elect_one()) tc_commit2_mc(&bars->acc2_full[buf], (uint16_t)3);
         }
         if (elect_one()) tc_commit2_mc(&bars->y1_empty[yb], (uint16_t)3);
+        if (p.proj) {
+          if (elect_one()) tc_commit2_mc(&bars->xempty[xs], (uint16_t)3);
+          if (++xs == 2) { xs = 0; xph ^= 1u; }
+        }
         it2++;
       };
       BT_TOTAL_BEGIN();
@@ -395,13 +428,13 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         if (held >= 0) {                             // hand the previous slot back once its store has read it
           if (lane == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive(&bars->rempty[held]);
+            if (!p.proj) mbar_arrive(&bars->rempty[held]);   // (projection mode: the slots are this warp's private staging)
           }
           held = -1;
         }
         BT_ADD(17, ta_);
         BT_WAIT(14, &bars->acc2_full[buf], (uint32_t)(u2 >> 1) & 1u);
-        BT_WAIT(15, &bars->rfull[slot], (uint32_t)(cidx / p.nr) & 1u);
+        if (!p.proj) BT_WAIT(15, &bars->rfull[slot], (uint32_t)(cidx / p.nr) & 1u);
         tc_fence_after();
         BT_T0(tb_);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(buf * 128 + sg * 64);
@@ -411,7 +444,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           const uint32_t a0 = srow + (uint32_t)(((2 * cc) ^ (row & 7)) << 4), a1 = srow + (uint32_t)(((2 * cc + 1) ^ (row & 7)) << 4);
-          const uint4 r0 = lds128(a0), r1 = lds128(a1);
+          uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+          if (!p.proj) { r0 = lds128(a0); r1 = lds128(a1); }
           tc_ld_wait();
           if (cc < 3) tc_ld16(taddr + (uint32_t)((cc + 1) * 16), v[(cc + 1) & 1]);
           const int col0 = n2 * 128 + sg * 64 + cc * 16;
@@ -478,7 +512,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
     if (held >= 0 && lane == 0) {
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      mbar_arrive(&bars->rempty[held]);
+      if (!p.proj) mbar_arrive(&bars->rempty[held]);
     }
     if (warp == 4) { BT_TOTAL_END(16); }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -543,10 +577,12 @@ extern "C" int odtk_bt_prof_read(unsigned long long *out, int reset) {
 #endif
 
 extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_) {
-  if (!d || !d->x || !d->w2 || !d->w3 || !d->residual || !d->y) return ODTK_E_INVALID;
+  if (!d || !d->x || !d->w2 || !d->w3 || !d->y) return ODTK_E_INVALID;
+  const bool proj = d->xproj != nullptr;
+  if (proj ? (!d->wproj || d->c1 != 64) : !d->residual) return ODTK_E_INVALID;
   if (d->n <= 0 || d->h <= 0 || d->width <= 0) return ODTK_E_INVALID;
   if ((d->c1 != 64 && d->c1 != 128) || d->c2 % 128 != 0 || d->c2 <= 0 || d->c2 > 512) return ODTK_E_UNSUPPORTED;
-  if (((uintptr_t)d->x | (uintptr_t)d->w2 | (uintptr_t)d->w3 | (uintptr_t)d->residual | (uintptr_t)d->y) & 15) return ODTK_E_INVALID;
+  if (((uintptr_t)d->x | (uintptr_t)d->w2 | (uintptr_t)d->w3 | (uintptr_t)d->residual | (uintptr_t)d->y | (uintptr_t)d->xproj | (uintptr_t)d->wproj) & 15) return ODTK_E_INVALID;
   if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
   cudaStream_t stream = (cudaStream_t)stream_;
   const BtDevice *ds = bt_device(stream);
@@ -567,10 +603,12 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   p.ppitch = pitch;
   p.patch_slot = (18 * pitch * 128 + 1023) / 1024 * 1024;
   p.w_resident = d->c1 == 64;
+  p.proj = proj ? 1 : 0;
   const int kc1 = d->c1 / 64, n2tiles = d->c2 / 128;
-  const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot;
-  if (p.w_resident && w_resident_bytes > 60 * 1024) p.w_resident = 0;
-  const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kBiasBytes + kBarBytes;
+  const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot + (proj ? n2tiles * kWSlot : 0);
+  if (p.w_resident && w_resident_bytes > 72 * 1024) p.w_resident = 0;
+  if (proj && !p.w_resident) return ODTK_E_UNSUPPORTED;
+  const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kBiasBytes + kBarBytes + (proj ? 2 * kRSlot : 0);
   // shared-memory budget: identity ring as deep as it gets (it carries the HBM stream), then the weight ring
   static int nw_min = -1;
   if (nw_min < 0) { const char *e = getenv("ODTK_BNECK_NW"); nw_min = e ? atoi(e) : 4; if (nw_min < 2 || nw_min > kMaxWSlots) nw_min = 4; }
@@ -578,6 +616,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   int left = kSmemMax - fixed - (p.w_resident ? w_resident_bytes : p.nw * kWSlot);
   p.nr = left / kRSlot;
   if (p.nr > nr_cap) p.nr = nr_cap;
+  if (proj && p.nr > 2) p.nr = (p.nr >= 4) ? 4 : 2;   // projection mode: the slots are the epilogue's private staging (even count)
   if (p.nr < 2) return ODTK_E_UNSUPPORTED;
   left -= p.nr * kRSlot;
   if (!p.w_resident) { p.nw += left / kWSlot; if (p.nw > kMaxWSlots) p.nw = kMaxWSlots; }
@@ -585,7 +624,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   p.relu = d->relu;
   p.b2 = d->b2; p.b3 = d->b3;
   const uint64_t C1 = (uint64_t)d->c1, C2 = (uint64_t)d->c2, H = (uint64_t)d->h, W = (uint64_t)d->width, N = (uint64_t)d->n;
-  CUtensorMap tmX, tmW2, tmW3, tmR, tmY;
+  CUtensorMap tmX, tmW2, tmW3, tmR, tmY, tmWd;
   {
     uint64_t dims[4] = {C1, H, W, N}, str[3] = {W * C1 * 2, C1 * 2, H * W * C1 * 2};
     uint32_t box[4] = {64, (uint32_t)p.ppitch, 18, 1};
@@ -604,7 +643,17 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   {
     uint64_t dims[4] = {C2, H, W, N}, str[3] = {W * C2 * 2, C2 * 2, H * W * C2 * 2};
     uint32_t boxR[4] = {64, 8, 16, 1}, boxY[4] = {64, 8, 4, 1};
-    if (!bt_encode(&tmR, d->residual, 4, dims, str, boxR) || !bt_encode(&tmY, d->y, 4, dims, str, boxY)) return ODTK_E_CUDA;
+    if (!bt_encode(&tmY, d->y, 4, dims, str, boxY)) return ODTK_E_CUDA;
+    if (!proj && !bt_encode(&tmR, d->residual, 4, dims, str, boxR)) return ODTK_E_CUDA;
+  }
+  tmWd = tmW3;
+  if (proj) {   // identity = xproj [n, h, width, 64] x wproj [c2, 64]^T, computed by the kernel
+    uint64_t dims[4] = {64, H, W, N}, str[3] = {W * 64 * 2, 64 * 2, H * W * 64 * 2};
+    uint32_t boxR[4] = {64, 8, 16, 1};
+    if (!bt_encode(&tmR, d->xproj, 4, dims, str, boxR)) return ODTK_E_CUDA;
+    uint64_t dimsW[2] = {64, C2}, strW[1] = {64 * 2};
+    uint32_t boxW[2] = {64, 64};
+    if (!bt_encode(&tmWd, d->wproj, 2, dimsW, strW, boxW)) return ODTK_E_CUDA;
   }
   const int sms = odtk_sm_count();
   const int npairs = (p.total_tiles + 1) / 2;
@@ -622,7 +671,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   cfg.numAttrs = 1;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, p);
+    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmWd, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

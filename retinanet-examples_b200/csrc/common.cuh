@@ -9,8 +9,13 @@
 
 static inline size_t odtk_align_up(size_t x) { return (x + ODTK_ALIGN - 1) / ODTK_ALIGN * ODTK_ALIGN; }
 
+// SM budget of the calling host thread's launches (0 = the whole device): persistent kernels size their grids from
+// odtk_sm_count(), so two streams given complementary budgets run their kernels side by side on disjoint SMs
+// (odtk_set_sm_budget, include/odtk_b200.h).  Defined in version.cu.
+extern int g_odtk_sm_budget;
+
 // SM count of the CURRENT device (cached per device ordinal; grids are sized from it, never from a constant)
-static inline int odtk_sm_count() {
+static inline int odtk_sm_count_device() {
   static int cache[64];
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -18,6 +23,10 @@ static inline int odtk_sm_count() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
   if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
+}
+static inline int odtk_sm_count() {
+  const int n = odtk_sm_count_device();
+  return (g_odtk_sm_budget > 0 && g_odtk_sm_budget < n) ? g_odtk_sm_budget : n;
 }
 
 // Monotone float -> uint32 key; larger key == larger float.  This is the transform

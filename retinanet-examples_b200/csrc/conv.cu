@@ -125,7 +125,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL2 ? 2 : 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], (TWO ? 2 : 1) * 32 * kEpiWarps); }
+    for (int b = 0; b < 2; b++) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], (TWO ? 2 : 1) * kEpiWarps /* one arrival per epilogue warp */); }
     mbar_init(&bars->res_full, 1); mbar_init(&bars->res_empty, 1); mbar_init(&bars->ident_full, 1);
     for (int s = 0; s < 3; s++) { mbar_init(&bars->patch_full[s], 1); mbar_init(&bars->patch_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -913,8 +913,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      if (TWO) mbar_arrive_remote(mapa_rank(smem_u32(&bars->tmem_empty[buf]), 0));   // the leader waits for both CTAs
-      else     mbar_arrive(&bars->tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) {   // one arrival per warp (256 remote arrivals per tile serialise on the leader's barrier)
+        if (TWO) mbar_arrive_remote(mapa_rank(smem_u32(&bars->tmem_empty[buf]), 0));   // the leader waits for both CTAs
+        else     mbar_arrive(&bars->tmem_empty[buf]);
+      }
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1141,7 +1144,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const DeviceState *dstate = device_state(stream);
   if (!dstate) return ODTK_E_CUDA;
-  const int g_num_sms = dstate->num_sms;
+  const int g_num_sms = odtk_sm_count();   // the launch budget (odtk_set_sm_budget) or the whole device
   ConvParams p;
   memset(&p, 0, sizeof p);
   p.N = d->n; p.H = d->h; p.W = d->width; p.Cin = d->cin; p.Cout = d->cout;
@@ -1477,7 +1480,7 @@ extern "C" int odtk_stem_conv(const void *xp, const void *w, const float *bias, 
   cudaStream_t stream = (cudaStream_t)stream_;
   const DeviceState *dstate = device_state(stream);
   if (!dstate) return ODTK_E_CUDA;
-  const int g_num_sms = dstate->num_sms;
+  const int g_num_sms = odtk_sm_count();   // the launch budget (odtk_set_sm_budget) or the whole device
   const int OH = h / 2, OW = width / 2, HP = h + 6, WP = width + 8;
   if ((long long)n * OH * OW >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
   ConvParams p;

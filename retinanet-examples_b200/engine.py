@@ -275,26 +275,36 @@ def stem_pool_padded(xp, h, wd, w, bias, cout, relu=True):
     return out
 
 
-def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None):
+def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None, wproj=None):
     """Tail of a stride-1 bottleneck block in one kernel (odtk_bottleneck_tail):
     relu(conv1x1(relu(conv3x3(x, w2) + b2), w3) + b3 + residual).  x: NHWC fp16 [N,H,W,C1] (C1 64 / 128); w2 packed
     [C1, 9*C1]; w3 packed [C2, C1]; residual NHWC fp16 [N,H,W,C2].  Returns NHWC fp16 [N,H,W,C2]."""
-    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous() and residual.is_contiguous()
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
     n, h, wd, c1 = x.shape
     c2 = w3.shape[0]
-    assert residual.shape == (n, h, wd, c2)
+    if xproj is not None:          # identity = xproj x wproj^T computed by the kernel (b3 already holds both biases)
+        assert xproj.is_contiguous() and xproj.shape == (n, h, wd, 64) and wproj.shape == (c2, 64)
+    else:
+        assert residual.is_contiguous() and residual.shape == (n, h, wd, c2)
     if out is None:
         out = torch.empty((n, h, wd, c2), dtype=torch.float16, device=x.device)
     d = _lib.BneckDesc()
-    d.x, d.w2, d.w3, d.residual, d.y = x.data_ptr(), w2.data_ptr(), w3.data_ptr(), residual.data_ptr(), out.data_ptr()
+    d.x, d.w2, d.w3, d.y = x.data_ptr(), w2.data_ptr(), w3.data_ptr(), out.data_ptr()
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.xproj = xproj.data_ptr() if xproj is not None else None
+    d.wproj = wproj.data_ptr() if wproj is not None else None
     d.b2 = b2.data_ptr() if b2 is not None else None
     d.b3 = b3.data_ptr() if b3 is not None else None
     d.n, d.h, d.width, d.c1, d.c2, d.relu = n, h, wd, c1, c2, int(relu)
     _lib.check(_lib.lib().odtk_bottleneck_tail(ctypes.byref(d), _stream()), "bottleneck_tail")
     STATS["launches"] += 1
     px = n * h * wd
-    _trace("bneck_tail", 2 * px * c1 * (9 * c1 + c2), px * (c1 + 2 * c2) * 2 + w2.numel() * 2 + w3.numel() * 2,
-           n=n, h=h, w=wd, cin=c1, cout=c2, residual=True)
+    if xproj is not None:
+        _trace("bneck_tail", 2 * px * (c1 * (9 * c1 + c2) + 64 * c2), px * (c1 + 64 + c2) * 2 + w2.numel() * 2 + w3.numel() * 2 + wproj.numel() * 2,
+               n=n, h=h, w=wd, cin=c1, cout=c2, upsample=False, residual=False)
+    else:
+        _trace("bneck_tail", 2 * px * c1 * (9 * c1 + c2), px * (c1 + 2 * c2) * 2 + w2.numel() * 2 + w3.numel() * 2,
+               n=n, h=h, w=wd, cin=c1, cout=c2, residual=True)
     return out
 
 

@@ -336,8 +336,23 @@ class Model:
         P = self._packed
         outs = {}
         for blk in P["blocks"]:
-            identity = x if blk["down"] is None else blk["down"](x)
             cs = blk["convs"]
+            dn = blk["down"]
+            if (self.fused_bneck and dn is not None and len(cs) == 3 and dn.ks == 1 and dn.stride == 1 and dn.cin == 64 and
+                    dn.groups == 1 and cs[1].stride == 1 and cs[1].groups == 1 and cs[1].ks == 3 and cs[1].cin == 64 and
+                    cs[1].cout == 64 and cs[2].cin == 64 and cs[2].cout == dn.cout and dn.cout % 128 == 0 and dn.cout <= 512):
+                # first block of layer1: conv2 + conv3 + the 1x1 PROJECTION of the block input (torchvision `downsample`)
+                # + ReLU in one kernel: neither the 3x3's output nor the projected identity touches HBM
+                if "b3d" not in blk:
+                    blk["b3d"] = (cs[2].b + dn.b).contiguous()
+                out = cs[0](x, relu=True)
+                px = out.shape[0] * out.shape[1] * out.shape[2]
+                engine.STATS["conv_flops"] += 2 * px * (64 * (9 * 64 + cs[2].cout) + 64 * dn.cout)
+                x = engine.bottleneck_tail(out, cs[1].w, cs[1].b, cs[2].w, blk["b3d"], None, relu=True, xproj=x, wproj=dn.w)
+                if blk["last"]:
+                    outs[blk["level"]] = x
+                continue
+            identity = x if dn is None else dn(x)
             if (self.fused_bneck and len(cs) == 3 and cs[1].stride == 1 and cs[1].groups == 1 and cs[1].ks == 3 and
                     cs[1].cin in (64, 128) and cs[1].cout == cs[1].cin and cs[2].cin == cs[1].cin and cs[2].cout % 128 == 0 and
                     cs[2].cout <= 512):

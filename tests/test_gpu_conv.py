@@ -372,3 +372,22 @@ def test_bottleneck_tail_fused_matches_torch_and_two_kernel_route(n, h, w, c1):
     y2 = engine.conv2d(mid_d, w3p, b3d, c2, 1, relu=True, residual=rd, bias_op=engine.pack_bias(b3d))
     err = (y.float() - y2.float()).abs().max().item()
     assert err <= 2e-3 * y2.float().abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 24, 48), (1, 9, 17), (3, 8, 16), (2, 200, 320)])
+def test_bottleneck_tail_with_projected_identity(n, h, w):
+    """First block of layer1: the identity is a 1x1 projection (torchvision `downsample`) of the 64-channel block input,
+    computed by the fused kernel on the tensor core instead of being read from HBM."""
+    c1, c2 = 64, 256
+    g = torch.Generator().manual_seed(n * 11 + h + w)
+    xin = _rand((n, h, w, 64), g)
+    x = _rand((n, h, w, c1), g)
+    w2, b2 = _rand((c1, c1, 3, 3), g, 0.04), torch.randn(c1, generator=g) * 0.5
+    w3, b3 = _rand((c2, c1, 1, 1), g, 0.08), torch.randn(c2, generator=g) * 0.5
+    wd, bd = _rand((c2, 64, 1, 1), g, 0.1), torch.randn(c2, generator=g) * 0.5
+    y = engine.bottleneck_tail(x.to(DEV), engine.pack_weight(w2.float()).to(DEV), b2.to(DEV), engine.pack_weight(w3.float()).to(DEV),
+                               (b3 + bd).to(DEV), None, relu=True, xproj=xin.to(DEV), wproj=engine.pack_weight(wd.float()).to(DEV))
+    torch.cuda.synchronize()
+    mid = _ref_conv(x, w2, b2, 3, relu=True).permute(0, 2, 3, 1).to(torch.float16)
+    ref = F.relu(_ref_conv(mid, w3, b3, 1) + _ref_conv(xin, wd, bd, 1))
+    _close16(y, ref)
