@@ -154,6 +154,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  grid_dep_launch_dependents();
+  grid_dep_wait();                // (the prologue above touched only constants: weights' descriptors, biases)
   const uint32_t tmem_base = bars->tmem_base;
 
   // work: pairs of consecutive tiles; the pair's second tile may be padding (odd total): computed, never stored
@@ -664,11 +666,13 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = odtk_pdl_on() ? 2 : 1;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
     cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmWd, p);

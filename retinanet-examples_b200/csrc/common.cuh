@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/odtk_b200.h"
 
@@ -23,6 +24,12 @@ static inline int odtk_sm_count_device() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
   if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
+}
+// ODTK_PDL=0 turns programmatic dependent launch off (A/B); default on
+static inline bool odtk_pdl_on() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("ODTK_PDL"); on = e ? atoi(e) : 1; }
+  return on != 0;
 }
 static inline int odtk_sm_count() {
   const int n = odtk_sm_count_device();

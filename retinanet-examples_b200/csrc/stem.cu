@@ -92,6 +92,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  grid_dep_launch_dependents();
+  grid_dep_wait();
   const uint32_t tmem_base = bars->tmem_base;
   const int per_img = p.tiles_h * p.tiles_w;
 
@@ -317,7 +319,17 @@ extern "C" int odtk_stem_pool(const void *xp, const void *w, const float *bias, 
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    stem_pool_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = odtk_pdl_on() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, stem_pool_kernel, tmA, tmB, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--tag", default="base")
     ap.add_argument("--rotated", action="store_true")
     ap.add_argument("--only", default=None, help="substring filter on the layer key")
+    ap.add_argument("--calibrated", action="store_true", help="class-head bias calibrated like bench.py (~0.56 %% of the scores above the threshold)")
     args = ap.parse_args()
     import torch
     from retinanet_examples_b200 import engine
@@ -51,7 +52,17 @@ def main():
 
     na = 27 if args.rotated else 9
     model = Model(args.backbone, classes=80, rotated_bbox=args.rotated)
-    model.load_state_dict(make_state_dict(args.backbone, 80, na, args.rotated, seed=0)).cuda(0)
+    sd = make_state_dict(args.backbone, 80, na, args.rotated, seed=0)
+    if args.calibrated:
+        from retinanet_examples_b200 import synth
+        xp = torch.randn((2, 3, 800, 1280), generator=torch.Generator().manual_seed(1)).to(torch.float16).contiguous(memory_format=torch.channels_last).to(dev)
+
+        def gpu_logits(s):
+            engine.STATS["trace"] = []
+            model.load_state_dict(s).cuda(0)
+            return model.forward_heads(xp, sigmoid=False)[0]
+        sd = synth.calibrate_cls_head(sd, gpu_logits)
+    model.load_state_dict(sd).cuda(0)
     model.parallel_heads = False
     x = torch.randn((args.batch, 3, 800, 1280), generator=torch.Generator().manual_seed(1)).to(torch.float16) \
         .contiguous(memory_format=torch.channels_last).to(dev)
