@@ -281,7 +281,7 @@ class FullWorkload:
                           "algorithmic_bytes_per_step": int(sum(l["bytes"] for l in self.trace)),
                           "note": "sum over the step's launches of max(FLOPs/tensor peak, operand+output bytes/HBM peak): "
                                   "the bound of layer-by-layer execution; frac_of_step = ideal / measured ms_per_step"}
-        return {"kernel": "conv_gemm_kernel + stem_pool_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
+        return {"kernel": "conv_gemm_kernel + bottleneck_tail_kernel + stem_pool_kernel (tcgen05, all %d conv launches of a step)" % (n // steps), "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the
                 # committed ncu capture of this workload (tools/capture_step.py -> profiles/r02_layer_table.json)
@@ -361,6 +361,11 @@ class PostprocWorkload:
         self.launches_per_step = 3 + 1   # filter, gather, select+decode (all levels), nms
         self.level_score_bytes = [c.numel() * 4 for c, _ in self.host]
         self.world_gather = None
+        # throughput mode: consecutive batches alternate between CUDA streams, so the HBM-bound score filter of batch k+1
+        # runs next to the latency-bound select + NMS of batch k (a few CTAs); per-batch latency is unchanged
+        self.nstreams = int(os.environ.get("ODTK_BENCH_POSTPROC_STREAMS", "2"))
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
+        self.k = 0
 
     def _run(self, tensors):
         from retinanet_examples_b200 import _C
@@ -369,7 +374,20 @@ class PostprocWorkload:
         return _C.nms(scores, boxes, classes, 0.5, self.det, self.rotated)
 
     def step(self):
-        self.out = self._run(self.dev)
+        if not self.streams:
+            self.out = self._run(self.dev)
+            return
+        torch = self.torch
+        main, side = torch.cuda.current_stream(), self.streams[self.k % self.nstreams]
+        self.k += 1
+        side.wait_stream(main)                    # ordered after whatever the caller enqueued (the timing start event)
+        with torch.cuda.stream(side):
+            self.out = self._run(self.dev)
+
+    def drain(self):
+        """The caller's stream waits for every batch still in flight (called before the timing end event)."""
+        for s in self.streams:
+            self.torch.cuda.current_stream().wait_stream(s)
 
     def step_e2e(self):
         torch = self.torch
@@ -384,7 +402,7 @@ class PostprocWorkload:
 
     def config(self):
         return {"workload": self.name, "images_per_gpu": self.batch, "top_n": 1000, "detections": 100,
-                "threshold": 0.05, "nms": 0.5,
+                "threshold": 0.05, "nms": 0.5, "batches_in_flight": max(1, self.nstreams),
                 "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2" % (self.h2d_bytes / 1e6)}
 
     def roofline(self, lib, peaks, steps):
@@ -446,6 +464,7 @@ def postproc_sub(device, peaks, lib, rotated=False, batch=8, steps=30):
     e0.record()
     for _ in range(steps):
         wl.step()
+    wl.drain()
     e1.record()
     torch.cuda.synchronize()
     lib.odtk_prof_enable(0)
@@ -453,7 +472,18 @@ def postproc_sub(device, peaks, lib, rotated=False, batch=8, steps=30):
     roof = wl.roofline(lib, peaks, steps)
     nms_ms, nms_n = _prof_get(lib, 2)
     sel_ms, sel_n = _prof_get(lib, 1)
+    # the same batches one after the other on one stream: the latency of a batch (what round 1 reported as us/image)
+    saved, wl.streams = wl.streams, []
+    e0.record()
+    for _ in range(steps):
+        wl.step()
+    e1.record()
+    torch.cuda.synchronize()
+    wl.streams = saved
+    serial_ms = e0.elapsed_time(e1)
     return {"workload": wl.name, "us_per_image": round(ms * 1e3 / steps / batch, 2), "images_per_gpu": batch, "steps": steps,
+            "batches_in_flight": max(1, wl.nstreams), "latency_us_per_batch": round(serial_ms * 1e3 / steps, 1),
+            "us_per_image_one_batch_at_a_time": round(serial_ms * 1e3 / steps / batch, 2),
             "images_per_sec": round(batch * steps / (ms * 1e-3), 1),
             "hbm_floor_us_per_image": round(sum(wl.level_score_bytes) / batch / (peaks["hbm"] * 1e9) * 1e6, 2),
             "nms_us_per_launch": round(nms_ms * 1e3 / max(nms_n, 1), 2), "select_decode_us_per_step": round(sel_ms * 1e3 / steps, 2),
@@ -525,6 +555,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if getattr(wl, "drain", None):
+            wl.drain()
         e1.record()
         barrier()
         t1 = time.time()

@@ -4,7 +4,7 @@
     compute-sanitizer --tool synccheck python tools/sanitize_cases.py
 Shapes are tiny (the tools slow kernels down 10-100x) but chosen to reach each variant: conv modes 0 / 1 / 3 / 4 / 5,
 2-CTA multicast pairs and cta_group::2 pairs (remote mbarrier arrives), resident weights, bias / residual / upsample on
-the tensor core, TMA-store epilogue, candidate epilogue, fused stem + pool, decode (filter / gather / select), NMS
+the tensor core, TMA-store epilogue, candidate epilogue, fused stem + pool, fused bottleneck tail (bottleneck.cu, all three modes), decode (filter / gather / select), NMS
 (shared-memory aliasing of the sort scratch), rotated NMS, iou, target assignment, the cooperative loss kernel."""
 import os
 import sys
@@ -50,6 +50,17 @@ def main():
         conv(2, 26, 40, 128, 128, 3, relu=True, stride=2)                  # parity-split stride 2
         conv(2, 25, 39, 256, 256, 3, relu=True, stride=2)                  # element-strided boxes
         conv(40, 100, 160, 64, 256, 1, relu=True)                          # enough tiles for 1x1
+        for c1, proj in ((64, False), (128, False), (64, True)):           # fused bottleneck tail: residual / streamed weights / projected identity
+            c2 = 4 * c1
+            xx, w2 = rnd(3, 9, 17, c1), engine.pack_weight(torch.randn((c1, c1, 3, 3), generator=g) * 0.05).to(DEV)
+            w3 = engine.pack_weight(torch.randn((c2, c1, 1, 1), generator=g) * 0.05).to(DEV)
+            b2, b3 = torch.randn(c1, generator=g).to(DEV), torch.randn(c2, generator=g).to(DEV)
+            if proj:
+                engine.bottleneck_tail(xx, w2, b2, w3, b3, None, xproj=rnd(3, 9, 17, 64), wproj=engine.pack_weight(torch.randn((c2, 64, 1, 1), generator=g) * 0.05).to(DEV))
+            else:
+                engine.bottleneck_tail(xx, w2, b2, w3, b3, rnd(3, 9, 17, c2))
+            torch.cuda.synchronize()
+            print("bottleneck_tail c1=%d proj=%s ok" % (c1, proj), flush=True)
         x = rnd(2, 64, 96, 3)
         wt, b = engine.pack_stem_weight(torch.randn((64, 3, 7, 7), generator=g) * 0.1).to(DEV), torch.randn(64, generator=g).to(DEV)
         engine.stem_pool(x, wt, b, 64)
