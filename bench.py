@@ -363,7 +363,7 @@ class PostprocWorkload:
         self.world_gather = None
         # throughput mode: consecutive batches alternate between CUDA streams, so the HBM-bound score filter of batch k+1
         # runs next to the latency-bound select + NMS of batch k (a few CTAs); per-batch latency is unchanged
-        self.nstreams = int(os.environ.get("ODTK_BENCH_POSTPROC_STREAMS", "2"))
+        self.nstreams = int(os.environ.get("ODTK_BENCH_POSTPROC_STREAMS", "3"))
         self.streams = [torch.cuda.Stream(device=device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
         self.k = 0
 
