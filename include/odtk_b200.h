@@ -235,6 +235,15 @@ int odtk_conv_map_cache_stats(long long *hits, long long *misses);
  * graph keeps the grids it was captured with.                                                                          */
 int odtk_set_sm_budget(int sms);
 
+/* Buffers shared between the GPU processes of one node (CUDA IPC): odtk_peer_alloc = cudaMalloc + zero fill + a 64-byte
+ * handle to send to the other ranks (any transport); odtk_peer_open maps a received handle into the CALLING process with
+ * its own device current, NVLink / NVSwitch peer access enabled -- the pointer is then valid in kernels of that device
+ * (the in-kernel detection gather, odtk_nms_gather); odtk_peer_close / odtk_peer_free undo them.                    */
+int odtk_peer_alloc(size_t bytes, void **ptr, void *handle64);
+int odtk_peer_open(const void *handle64, void **ptr);
+int odtk_peer_close(void *ptr);
+int odtk_peer_free(void *ptr);
+
 /* Tail of a stride-1 ResNet bottleneck block in ONE kernel (torchvision Bottleneck.forward behind
  * odtk/backbones/resnet.py:24-39; the reference runs it as two cuDNN convolutions + an elementwise add):
  *     y = relu( conv1x1( relu( conv3x3(x, w2) + b2 ), w3 ) + b3 + residual )

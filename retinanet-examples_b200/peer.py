@@ -4,7 +4,9 @@ Replaces the all_gathers of the reference's odtk/infer.py:98-102 (five NCCL coll
 single host-launched ncclAllGather per step; the exchange is part of the step's kernels, so it sits inside the CUDA graph.
 
 One process per GPU (torch.distributed initialised, any backend -- it only carries the 64-byte IPC handles once).
-Buffers are ordinary torch CUDA tensors shared through CUDA IPC (torch's own cudaIpcGetMemHandle / OpenMemHandle path)."""
+The buffers are plain cudaMalloc memory shared through CUDA IPC by the library itself (odtk_peer_alloc / odtk_peer_open):
+each rank opens its peers' handles with ITS OWN device current, which maps them into its address space with NVLink peer
+access enabled."""
 import ctypes
 
 import torch
@@ -13,16 +15,11 @@ import torch.distributed as dist
 from . import _lib
 
 
-def _export(t):
-    """(ipc description of the tensor's storage, byte offset of the tensor inside it)."""
-    st = t.untyped_storage()
-    return st._share_cuda_(), t.storage_offset() * t.element_size()
+class _DevArray:
+    """Zero-copy view of raw device memory for torch (the CUDA array interface)."""
 
-
-def _import(desc, nbytes, device):
-    handle, offset = desc
-    st = torch.UntypedStorage._new_shared_cuda(*handle)
-    return torch.empty(0, dtype=torch.uint8, device=device).set_(st, offset, (nbytes,))
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
 
 class PeerGather:
@@ -38,23 +35,32 @@ class PeerGather:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.row = self.det * (2 + self.nbox)
         half = self.world * self.batch * self.row
-        self.buf = torch.zeros(2 * half, dtype=torch.float32, device=self.device)          # two parity halves
-        self.flags = torch.zeros(self.world, dtype=torch.int32, device=self.device)        # arrival counters, by source rank
+        L = _lib.lib()
+        # one allocation per rank: [ two parity halves of the gather buffer | arrival counters, one per source rank ]
+        self._buf_bytes = (2 * half * 4 + 255) // 256 * 256
+        nbytes = self._buf_bytes + 256
+        self._base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(L.odtk_peer_alloc(nbytes, ctypes.byref(self._base), handle), "peer_alloc")
+        self.buf = torch.as_tensor(_DevArray(self._base.value, 2 * half, "<f4"), device=self.device)
+        self.flags = torch.as_tensor(_DevArray(self._base.value + self._buf_bytes, self.world, "<i4"), device=self.device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
-        torch.cuda.synchronize(self.device)
-        mine = (_export(self.buf), _export(self.flags))
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=group)
-        self._peers = []
+        dist.all_gather_object(everyone, bytes(handle), group=group)
+        self._opened = []
         self.desc = _lib.Gather()
         for r in range(self.world):
             if r == self.rank:
-                pb, pf = self.buf, self.flags
+                base = self._base.value
             else:
-                pb = _import(everyone[r][0], self.buf.numel() * 4, self.device)
-                pf = _import(everyone[r][1], self.world * 4, self.device)
-            self._peers.append((pb, pf))
-            self.desc.packed[r], self.desc.flags[r] = pb.data_ptr(), pf.data_ptr()
+                p = ctypes.c_void_p()
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r])
+                with torch.cuda.device(self.device):
+                    _lib.check(L.odtk_peer_open(h, ctypes.byref(p)), "peer_open (rank %d)" % r)
+                self._opened.append(p.value)
+                base = p.value
+            self.desc.packed[r], self.desc.flags[r] = base, base + self._buf_bytes
         self.desc.epoch = self.epoch.data_ptr()
         self.desc.num_peers, self.desc.rank = self.world, self.rank
         self.steps = 0                                   # host mirror of the device step counter
@@ -66,3 +72,13 @@ class PeerGather:
         k = (self.steps - 1) if step is None else step
         half = self.world * self.batch * self.row
         return self.buf[(k & 1) * half:(k & 1) * half + half].view(self.world * self.batch, self.det, 2 + self.nbox)
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (after every rank is done with them: barrier first)."""
+        L = _lib.lib()
+        for p in self._opened:
+            L.odtk_peer_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self._base is not None and self._base.value:
+            L.odtk_peer_free(self._base)
+            self._base = None
