@@ -623,7 +623,7 @@ def main():
     units = wl.units_per_step() * world
     cfg = wl.config()
     cfg.update({"global_batch": units,
-                "parallelism": ("image-wise sharding over %d GPUs, one NCCL all-gather of the packed detections per step" % world)
+                "parallelism": ("image-wise sharding over %d GPUs, detections of all ranks delivered to every rank each step (see config.gather)" % world)
                 if world > 1 else "single GPU"})
     out = {
         "metric": wl.metric, "value": round(units * args.steps / (ms * 1e-3), 2), "unit": "images/sec",
