@@ -200,7 +200,7 @@ typedef struct {
   const void *residual; /* NHWC fp16 [n, h, width, ldr] added before ReLU, or NULL      */
   const void *upsample; /* NHWC fp16 [n, h/2, width/2, cout] nearest-upsampled and added */
   void *y;
-  int n, h, width, cin, cout, ksize, relu, out_mode, ldy, ldr;
+  int n, h, width, cin, cout, ksize, relu /* 0 none, 1 ReLU, 2 ReLU6 (NHWC fp16 output only) */, out_mode, ldy, ldr;
   int stride;           /* 0/1, or 2: stride-2 conv (pad ksize/2); y is [n, (h-1)/2+1, (width-1)/2+1, ...] */
   const void *bias_op;  /* optional: bias packed by odtk_conv_pack_bias ([cout, 64] fp16).  When given, the
                            bias is added by ONE extra K block on the tensor core instead of in the epilogue */
@@ -283,6 +283,12 @@ int odtk_stem_conv(const void *xp, const void *w, const float *bias, void *y, in
  * odtk_maxpool3x3s2 (the same fp16 values are pooled).                                                        */
 int odtk_stem_pool(const void *xp, const void *w, const float *bias, void *y, int n, int h, int width, int cout,
                    int relu, odtk_stream_t stream);
+/* Depthwise 3x3 convolution, pad 1, stride 1 / 2, + bias + activation (act: 0 none, 1 ReLU, 2 ReLU6): the middle layer of
+ * MobileNetV2's inverted residual blocks (torchvision InvertedResidual behind odtk/backbones/mobilenet.py:5-25).
+ * x: NHWC fp16 [n, h, width, c], c % 8 == 0; w: fp16 [9, c] (tap-major); bias: fp32 [c] or NULL;
+ * y: NHWC fp16 [n, (h-1)/stride+1, (width-1)/stride+1, c].                                                        */
+int odtk_depthwise3x3(const void *x, const void *w, const float *bias, void *y, int n, int h, int width, int c,
+                      int stride, int act, odtk_stream_t stream);
 /* y = max(x, 0), fp16, n % 8 == 0, 16-byte aligned (input of FPN pyramid7: ReLU(P6), odtk/backbones/fpn.py:55). */
 int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t stream);
 /* 3-D strided copy (+ ReLU when relu != 0) of n x rows runs of row_elems fp16 (pitches in elements, everything a multiple

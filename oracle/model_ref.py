@@ -56,7 +56,37 @@ def _cb(sd, pconv, pbn, x, stride=1, padding=0, fp16=False, groups=1):
     return F.conv2d(x, w.half().float(), b, stride=stride, padding=padding, groups=groups)
 
 
+# MobileNetV2 (odtk/backbones/mobilenet.py:5-25 over torchvision mobilenetv2.py: features[0] 3x3 s2 conv + BN + ReLU6,
+# features[1..17] InvertedResidual = [1x1 expand + BN + ReLU6 unless t == 1] + depthwise 3x3 + BN + ReLU6 + 1x1 project + BN,
+# residual when stride 1 and cin == cout; FPN taps after features[6], [13], [17] (fpn.py:92-93))
+MOBILENET = {"MobileNetV2FPN": [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]}
+
+
+def _features_mobilenet(sd, backbone, x, fp16):
+    f = "backbones.%s.features.features." % backbone
+    x = _q(x, fp16)
+    x = _q(F.relu6(_cb(sd, f + "0.0", f + "0.1", x, 2, 1, fp16)), fp16)
+    taps, cin, idx = {}, 32, 1
+    for t, c, n, s in MOBILENET[backbone]:
+        for i in range(n):
+            stride, p, k = (s if i == 0 else 1), f + "%d.conv." % idx, 0
+            h = x
+            if t != 1:
+                h = _q(F.relu6(_cb(sd, p + "0.0", p + "0.1", h, 1, 0, fp16)), fp16)
+                k = 1
+            h = _q(F.relu6(_cb(sd, p + "%d.0" % k, p + "%d.1" % k, h, stride, 1, fp16, groups=h.shape[1])), fp16)
+            h = _cb(sd, p + "%d" % (k + 1), p + "%d" % (k + 2), h, 1, 0, fp16)
+            x = _q(h + x if (stride == 1 and cin == c) else h, fp16)
+            if idx in (6, 13, 17):
+                taps[idx] = x
+            cin, idx = c, idx + 1
+    return taps[6], taps[13], taps[17]
+
+
 def features(sd, backbone, x, fp16=False):
+    if backbone in MOBILENET:
+        c3, c4, c5 = _features_mobilenet(sd, backbone, x, fp16)
+        return _fpn(sd, backbone, c3, c4, c5, fp16)
     block, layers = LAYERS[backbone]
     f = "backbones.%s.features." % backbone
     x = _q(x, fp16)
@@ -85,6 +115,10 @@ def features(sd, backbone, x, fp16=False):
         if li >= 1:
             outs.append(x)
     c3, c4, c5 = outs
+    return _fpn(sd, backbone, c3, c4, c5, fp16)
+
+
+def _fpn(sd, backbone, c3, c4, c5, fp16):
     n = "backbones.%s." % backbone
     p5 = _q(_cb(sd, n + "lateral5", None, c5, 1, 0, fp16), fp16)
     p4 = _q(F.interpolate(p5, scale_factor=2) + _cb(sd, n + "lateral4", None, c4, 1, 0, fp16), fp16)

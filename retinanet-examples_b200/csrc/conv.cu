@@ -786,6 +786,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const __half2 z = __float2half2_rn(0.0f);
 #pragma unroll
                 for (int j = 0; j < 4; j++) { q0[j] = __hmax2(q0[j], z); q1[j] = __hmax2(q1[j], z); }
+                if (p.relu == 2) {   // ReLU6 (MobileNetV2, odtk/backbones/mobilenet.py): 6.0 is exact in fp16
+                  const __half2 six = __float2half2_rn(6.0f);
+#pragma unroll
+                  for (int j = 0; j < 4; j++) { q0[j] = __hmin2(q0[j], six); q1[j] = __hmin2(q1[j], six); }
+                }
               }
               sts128(srow + u0, o0);
               sts128(srow + u1, o1);
@@ -1182,6 +1187,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
       return ODTK_E_UNSUPPORTED;
   }
   if (d->out_mode < 0 || d->out_mode > 3) return ODTK_E_INVALID;
+  if (d->relu == 2 && d->out_mode != ODTK_OUT_NHWC_F16) return ODTK_E_UNSUPPORTED;   // ReLU6 only on fp16 activations
   if (d->out_mode == ODTK_OUT_NHWC_F16 && (d->cout % 16)) return ODTK_E_UNSUPPORTED;
   if (d->out_mode != ODTK_OUT_NHWC_F16 && (d->residual || d->upsample)) return ODTK_E_UNSUPPORTED;
   if ((long long)d->n * d->h * d->width >= (1ll << 31)) return ODTK_E_UNSUPPORTED;
@@ -1371,7 +1377,7 @@ extern "C" int odtk_conv2d(const odtk_conv_t *d, odtk_stream_t stream_) {
   CUtensorMap tmC = tmB;
   static int tma_store_on = -1;
   if (tma_store_on < 0) { const char *e = getenv("ODTK_CONV_TMA_STORE"); tma_store_on = e ? atoi(e) : 1; }
-  if (tma_store_on && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN > 128 && d->cout % 64 == 0) {
+  if (tma_store_on && p.mode == 0 && p.out_mode == ODTK_OUT_NHWC_F16 && BN > 128 && (BN % 64) == 0 && d->cout % 64 == 0) {   // 64-column store boxes must not reach into the next N tile
     uint64_t dims[2] = {(uint64_t)p.ldy, (uint64_t)p.M};
     uint64_t str[1] = {(uint64_t)p.ldy * 2};
     uint32_t box[2] = {64, 32};

@@ -269,6 +269,67 @@ extern "C" int odtk_preprocess_u8(const void *x, void *y, int n, int h, int w, i
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }
 
+// Depthwise 3x3 convolution (MobileNetV2's inverted residual blocks, torchvision mobilenetv2.py InvertedResidual behind
+// odtk/backbones/mobilenet.py:5-25), pad 1, stride 1 / 2, + bias (folded BatchNorm) + ReLU6.  NHWC fp16, 8 channels per
+// thread (16-byte loads), fp32 accumulation in tap order; w: [9][c] fp16.  No contraction over channels: HBM / L2-bound.
+__global__ void depthwise3x3_kernel(const __half *__restrict__ x, const __half *__restrict__ w, const float *__restrict__ bias,
+                                    __half *__restrict__ y, int n, int h, int wd, int c, int oh, int ow, int stride, int act) {
+  const int c8 = c >> 3;
+  const long long total = (long long)n * oh * ow * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c8);
+    long long pix = i / c8;
+    const int ox = (int)(pix % ow);
+    pix /= ow;
+    const int oy = (int)(pix % oh), img = (int)(pix / oh);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int iy = oy * stride + r - 1;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        const int ix = ox * stride + s - 1;
+        if (ix < 0 || ix >= wd) continue;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)img * h + iy) * wd + ix) * c + cc * 8));
+        const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(w + (long long)(r * 3 + s) * c + cc * 8));
+        const __half2 *xh = reinterpret_cast<const __half2 *>(&xv), *wh = reinterpret_cast<const __half2 *>(&wv);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 a = __half22float2(xh[j]), b = __half22float2(wh[j]);
+          acc[2 * j] = fmaf(a.x, b.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(a.y, b.y, acc[2 * j + 1]);
+        }
+      }
+    }
+    uint4 o;
+    __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float a = acc[2 * j] + (bias ? __ldg(bias + cc * 8 + 2 * j) : 0.0f), b = acc[2 * j + 1] + (bias ? __ldg(bias + cc * 8 + 2 * j + 1) : 0.0f);
+      if (act) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+      if (act == 2) { a = fminf(a, 6.0f); b = fminf(b, 6.0f); }
+      oh2[j] = __floats2half2_rn(a, b);
+    }
+    *reinterpret_cast<uint4 *>(y + (((long long)img * oh + oy) * ow + ox) * c + cc * 8) = o;
+  }
+}
+
+extern "C" int odtk_depthwise3x3(const void *x, const void *w, const float *bias, void *y, int n, int h, int width, int c,
+                                 int stride, int act, odtk_stream_t stream_) {
+  if (!x || !w || !y || n <= 0 || h <= 0 || width <= 0 || c <= 0 || (c % 8) || (stride != 1 && stride != 2) || act < 0 || act > 2)
+    return ODTK_E_INVALID;
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return ODTK_E_INVALID;
+  const int oh = (h - 1) / stride + 1, ow = (width - 1) / stride + 1;
+  const long long total = (long long)n * oh * ow * (c / 8);
+  OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);
+  depthwise3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)x, (const __half *)w, bias, (__half *)y, n, h,
+                                                                              width, c, oh, ow, stride, act);
+  return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
+}
+
 extern "C" int odtk_relu_f16(const void *x, void *y, long long n, odtk_stream_t stream_) {
   if (!x || !y || n <= 0 || (n % 8) || (((uintptr_t)x | (uintptr_t)y) & 15)) return ODTK_E_INVALID;
   OdtkProfScope prof(ODTK_PROF_LAYER, (cudaStream_t)stream_);

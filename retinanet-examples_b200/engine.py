@@ -308,6 +308,21 @@ def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None
     return out
 
 
+def depthwise3x3(x, w, bias, stride=1, act=2):
+    """Depthwise 3x3 (pad 1) + bias + activation (act: 0 none, 1 ReLU, 2 ReLU6) -- odtk_depthwise3x3.
+    x: NHWC fp16 [N,H,W,C]; w: fp16 [9, C]; bias fp32 [C]."""
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous()
+    n, h, wd, c = x.shape
+    oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    out = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().odtk_depthwise3x3(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+                                            ctypes.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                            ctypes.c_void_p(out.data_ptr()), n, h, wd, c, int(stride), int(act), _stream()), "depthwise3x3")
+    STATS["launches"] += 1
+    _trace("depthwise3x3", 2 * out.numel() * 9, x.numel() * 2 + out.numel() * 2 + w.numel() * 2, n=n, h=h, w=wd, cin=c, cout=c, stride=int(stride))
+    return out
+
+
 def pad_input(x):
     """NHWC fp16 RGB batch [N,H,W,3] -> zero-bordered NHWC4 [N, H+6, W+8, 4] (the stem kernels' input layout)."""
     n, h, wd, c = x.shape

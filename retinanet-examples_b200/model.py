@@ -27,11 +27,59 @@ RESNET_LAYERS = {"ResNet18FPN": ("basic", [2, 2, 2, 2]), "ResNet34FPN": ("basic"
                  "ResNeXt50_32x4dFPN": ("bottleneck", [3, 4, 6, 3]), "ResNeXt101_32x8dFPN": ("bottleneck", [3, 4, 23, 3])}
 # grouped bottlenecks (odtk/backbones/fpn.py:85-91): (groups, width_per_group); conv2 has planes * width_per_group / 64 * groups channels
 RESNEXT = {"ResNeXt50_32x4dFPN": (32, 4), "ResNeXt101_32x8dFPN": (32, 8)}
+# MobileNetV2 (odtk/backbones/mobilenet.py:5-25, fpn.py:92-93; torchvision mobilenetv2.py inverted_residual_setting):
+# (expansion t, output channels c, repeats n, first stride s); FPN taps features[6 / 13 / 17] = 32 / 96 / 320 channels
+MOBILENET = {"MobileNetV2FPN": [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]}
+MOBILENET_TAPS = (6, 13, 17)
+BACKBONES = tuple(RESNET_LAYERS) + tuple(MOBILENET)
+
+
+def mobilenet_blocks(backbone):
+    """[(features index, cin, cout, stride, t)] of the inverted residual blocks (features[1 .. 17])."""
+    out, cin, idx = [], 32, 1
+    for t, c, n, s in MOBILENET[backbone]:
+        for i in range(n):
+            out.append((idx, cin, c, s if i == 0 else 1, t))
+            cin, idx = c, idx + 1
+    return out
+
+
+def _head_specs(classes, num_anchors, rotated):
+    specs = []
+    nbox = 6 if rotated else 4
+    for head, out in (("cls_head", classes * num_anchors), ("box_head", nbox * num_anchors)):
+        for i in (0, 2, 4, 6):
+            specs.append(("%s.%d" % (head, i), "convb", (256, 256, 3, 3)))
+        specs.append(("%s.8" % head, "convb_final", (out, 256, 3, 3)))
+    return specs
+
+
+def _fpn_specs(n, ch):
+    return [(n + "lateral3", "convb", (256, ch[0], 1, 1)), (n + "lateral4", "convb", (256, ch[1], 1, 1)),
+            (n + "lateral5", "convb", (256, ch[2], 1, 1)), (n + "pyramid6", "convb", (256, ch[2], 3, 3)),
+            (n + "pyramid7", "convb", (256, 256, 3, 3)), (n + "smooth3", "convb", (256, 256, 3, 3)),
+            (n + "smooth4", "convb", (256, 256, 3, 3)), (n + "smooth5", "convb", (256, 256, 3, 3))]
+
+
+def mobilenet_specs(backbone, classes, num_anchors, rotated):
+    f = "backbones.%s.features.features." % backbone       # FPN.features = MobileNet module, MobileNet.features = Sequential
+    specs = [(f + "0.0", "conv", (32, 3, 3, 3)), (f + "0.1", "bn", 32)]
+    for idx, cin, cout, stride, t in mobilenet_blocks(backbone):
+        hidden, k = cin * t, 0
+        p = f + "%d.conv." % idx
+        if t != 1:
+            specs += [(p + "0.0", "conv", (hidden, cin, 1, 1)), (p + "0.1", "bn", hidden)]
+            k = 1
+        specs += [(p + "%d.0" % k, "conv", (hidden, 1, 3, 3)), (p + "%d.1" % k, "bn", hidden),
+                  (p + "%d" % (k + 1), "conv", (cout, hidden, 1, 1)), (p + "%d" % (k + 2), "bn_last", cout)]
+    return specs + _fpn_specs("backbones.%s." % backbone, [32, 96, 320]) + _head_specs(classes, num_anchors, rotated)
 
 
 def conv_specs(backbone, classes=80, num_anchors=9, rotated=False):
     """Every convolution / batch-norm of the model as (state_dict prefix, kind, shape info), in
     forward order.  kind: 'conv' (weight only, followed by 'bn') or 'convb' (weight + bias)."""
+    if backbone in MOBILENET:
+        return mobilenet_specs(backbone, classes, num_anchors, rotated)
     block, layers = RESNET_LAYERS[backbone]
     f = "backbones.%s.features." % backbone
     specs = [(f + "conv1", "conv", (64, 3, 7, 7)), (f + "bn1", "bn", 64)]
@@ -151,8 +199,8 @@ class Model:
             if len(backbones) != 1:
                 raise ValueError("one backbone per model on the B200 path")
             backbones = backbones[0]
-        if backbones not in RESNET_LAYERS:
-            raise ValueError("unsupported backbone %r (hot path: %s)" % (backbones, ", ".join(RESNET_LAYERS)))
+        if backbones not in BACKBONES:
+            raise ValueError("unsupported backbone %r (hot path: %s)" % (backbones, ", ".join(BACKBONES)))
         self.backbone = backbones
         self.name = 'RetinaNet'
         self.exporting = False
@@ -283,6 +331,10 @@ class Model:
         def conv_b(prefix, stride=1):
             return _Conv(sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride, dev)
 
+        if self.backbone in MOBILENET:
+            self._pack_mobilenet(P)
+            self._packed = P
+            return
         block, layers = RESNET_LAYERS[self.backbone]
         f = "backbones.%s.features." % self.backbone
         P["stem"] = conv_bn(f + "conv1", f + "bn1", 2)
@@ -310,10 +362,80 @@ class Model:
             P[head] = [conv_b("%s.%d" % (head, i)) for i in (0, 2, 4, 6, 8)]
         self._packed = P
 
+    def _pack_mobilenet(self, P):
+        """MobileNetV2FPN (odtk/backbones/mobilenet.py, fpn.py:92-93).  The tensor-core kernels work on 64-channel K
+        blocks: every activation is carried with its channel count padded to a multiple of 64 (zero weights / zero bias in
+        the padding, so the padding stays exactly 0 through ReLU6 and the residual adds)."""
+        sd, dev = self._sd, self.device
+        f = "backbones.%s.features.features." % self.backbone
+
+        def up64(c):
+            return (c + 63) // 64 * 64
+
+        def fold(pc, pb):
+            return engine.fold_bn(sd[pc + ".weight"], sd[pb + ".weight"], sd[pb + ".bias"], sd[pb + ".running_mean"], sd[pb + ".running_var"])
+
+        def padded_conv(w, b, stride=1, pad_in=True):
+            cout, cin = w.shape[0], w.shape[1]
+            wp = w.new_zeros((up64(cout), up64(cin) if pad_in else cin, w.shape[2], w.shape[3]))
+            wp[:cout, :cin] = w
+            bp = b.new_zeros(up64(cout))
+            bp[:cout] = b
+            return _Conv(wp, bp, stride, dev)
+
+        P["stem"] = padded_conv(*fold(f + "0.0", f + "0.1"), stride=2, pad_in=False)       # 3x3 s2, 3 -> 32: receptive-field gather + GEMM
+        blocks = []
+        for idx, cin, cout, stride, t in mobilenet_blocks(self.backbone):
+            p, k = f + "%d.conv." % idx, 0
+            blk = {"idx": idx, "stride": stride, "res": stride == 1 and cin == cout, "expand": None}
+            if t != 1:
+                blk["expand"] = padded_conv(*fold(p + "0.0", p + "0.1"))
+                k = 1
+            wd, bd = fold(p + "%d.0" % k, p + "%d.1" % k)                                 # depthwise [hidden, 1, 3, 3]
+            hidden = wd.shape[0]
+            wdp = wd.new_zeros((9, up64(hidden)))
+            wdp[:, :hidden] = wd.reshape(hidden, 9).t()
+            bdp = bd.new_zeros(up64(hidden))
+            bdp[:hidden] = bd
+            blk["dw_w"], blk["dw_b"] = wdp.to(torch.float16).contiguous().to(dev), bdp.float().contiguous().to(dev)
+            blk["hidden"] = hidden
+            blk["project"] = padded_conv(*fold(p + "%d" % (k + 1), p + "%d" % (k + 2)))
+            blocks.append(blk)
+        P["blocks"] = blocks
+        n = "backbones.%s." % self.backbone
+        for kname in ("lateral3", "lateral4", "lateral5"):
+            P[kname] = padded_conv(sd[n + kname + ".weight"], sd[n + kname + ".bias"])
+        for kname in ("smooth3", "smooth4", "smooth5"):
+            P[kname] = _Conv(sd[n + kname + ".weight"], sd.get(n + kname + ".bias"), 1, dev)
+        P["pyramid6"] = _Conv(sd[n + "pyramid6.weight"], sd.get(n + "pyramid6.bias"), 2, dev)
+        P["pyramid7"] = _Conv(sd[n + "pyramid7.weight"], sd.get(n + "pyramid7.bias"), 2, dev)
+        for head in ("cls_head", "box_head"):
+            P[head] = [_Conv(sd["%s.%d.weight" % (head, i)], sd.get("%s.%d.bias" % (head, i)), 1, dev) for i in (0, 2, 4, 6, 8)]
+
+    def _features_mobilenet(self, x):
+        """`x`: NHWC fp16 image [N, H, W, 3].  torchvision MobileNetV2.features[0 .. 17] with ReLU6, taps after blocks
+        6 / 13 / 17 (odtk/backbones/mobilenet.py:18-25), then the shared FPN."""
+        P = self._packed
+        x = P["stem"](x, relu=2)
+        outs = {}
+        for blk in P["blocks"]:
+            inp = x
+            hcur = blk["expand"](x, relu=2) if blk["expand"] is not None else x
+            engine.STATS["conv_flops"] += 2 * hcur.shape[0] * ((hcur.shape[1] - 1) // blk["stride"] + 1) * ((hcur.shape[2] - 1) // blk["stride"] + 1) * blk["hidden"] * 9
+            hcur = engine.depthwise3x3(hcur, blk["dw_w"], blk["dw_b"], blk["stride"], act=2)
+            x = blk["project"](hcur, relu=False, residual=inp if blk["res"] else None)
+            if blk["idx"] in MOBILENET_TAPS:
+                outs[blk["idx"]] = x
+        return self._fpn(outs[6], outs[13], outs[17])
+
     # ---- forward ---------------------------------------------------------------------------------
     def _stem(self, x=None, padded=None):
         """conv1 + bn1 + relu + maxpool (odtk/backbones/resnet.py:25-28).  One fused kernel when the stem has the
         standard 64 output channels and the image size is even; `padded` = (xp, h, w) from engine.preprocess_u8."""
+        if self.backbone in MOBILENET:
+            if padded is not None:
+                raise RuntimeError("the fused uint8 input path feeds the ResNet stem; pass a float / half image to MobileNetV2FPN")
+            return x                                        # the 3x3 stem runs inside _features_mobilenet
         stem = self._packed["stem"]
         if padded is not None:
             xp, h, w = padded
@@ -333,6 +455,8 @@ class Model:
 
     def _features(self, x):
         """`x`: the POOLED stem output [N, H/4, W/4, 64] (from _stem)."""
+        if self.backbone in MOBILENET:
+            return self._features_mobilenet(x)
         P = self._packed
         outs = {}
         for blk in P["blocks"]:
@@ -368,8 +492,11 @@ class Model:
                 x = cs[-1](out, relu=True, residual=identity)
             if blk["last"]:
                 outs[blk["level"]] = x
-        c3, c4, c5 = outs[3], outs[4], outs[5]
-        # FPN (odtk/backbones/fpn.py:45-61)
+        return self._fpn(outs[3], outs[4], outs[5])
+
+    def _fpn(self, c3, c4, c5):
+        """FPN (odtk/backbones/fpn.py:45-61) on the three backbone taps."""
+        P = self._packed
         p5 = P["lateral5"](c5)
         p4 = P["lateral4"](c4, upsample=p5)
         p3 = P["lateral3"](c3, upsample=p4)

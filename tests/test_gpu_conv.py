@@ -391,3 +391,35 @@ def test_bottleneck_tail_with_projected_identity(n, h, w):
     mid = _ref_conv(x, w2, b2, 3, relu=True).permute(0, 2, 3, 1).to(torch.float16)
     ref = F.relu(_ref_conv(mid, w3, b3, 1) + _ref_conv(xin, wd, bd, 1))
     _close16(y, ref)
+
+
+@pytest.mark.parametrize("n,h,w,c,stride", [(2, 16, 24, 64, 1), (1, 25, 39, 192, 2), (3, 7, 10, 384, 1), (1, 100, 160, 192, 2)])
+def test_depthwise3x3_relu6_matches_torch(n, h, w, c, stride):
+    """Depthwise 3x3 + bias + ReLU6 (MobileNetV2's inverted residual blocks): fp16 operands, fp32 accumulation."""
+    g = torch.Generator().manual_seed(h * 7 + w + c)
+    x, wt, b = _rand((n, h, w, c), g, 2.0), _rand((c, 1, 3, 3), g, 0.5), torch.randn(c, generator=g)
+    wp = wt.float().reshape(c, 9).t().contiguous().to(torch.float16)
+    y = engine.depthwise3x3(x.to(DEV), wp.to(DEV), b.to(DEV), stride=stride, act=2)
+    ref = F.relu6(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=stride, padding=1, groups=c))
+    _close16(y, ref)
+
+
+def test_conv1x1_relu6_epilogue():
+    g = torch.Generator().manual_seed(77)
+    x, wt, b = _rand((2, 13, 20, 128), g, 2.0), _rand((192, 128, 1, 1), g, 0.2), torch.randn(192, generator=g) * 3
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, 192, 1, relu=2, bias_op=engine.pack_bias(bd))
+    ref = F.relu6(_ref_conv(x, wt, b, 1))
+    assert float(ref.max()) == 6.0 and float(ref.min()) == 0.0       # both clamps are exercised
+    _close16(y, ref)
+
+
+def test_conv1x1_n_tile_not_a_multiple_of_64():
+    """Cout = 960 (MobileNetV2's widest expansion) splits into four 240-column N tiles: the TMA-store epilogue's 64-column
+    boxes would reach into the neighbouring tile, so this shape must take the row-store epilogue."""
+    g = torch.Generator().manual_seed(960)
+    x, wt, b = _rand((1, 4, 4, 192), g), _rand((960, 192, 1, 1), g, 0.1), torch.randn(960, generator=g)
+    bd = b.to(DEV)
+    y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, 960, 1, relu=2, bias_op=engine.pack_bias(bd))
+    assert engine.last_plan()["bn"] == 240 and engine.last_plan()["tma_store"] == 0
+    _close16(y, F.relu6(_ref_conv(x, wt, b, 1)))

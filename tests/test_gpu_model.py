@@ -22,7 +22,7 @@ def _rel_err(got, ref):
     return float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("backbone", ["ResNet18FPN", "ResNet50FPN", "ResNeXt50_32x4dFPN"])
+@pytest.mark.parametrize("backbone", ["ResNet18FPN", "ResNet50FPN", "ResNeXt50_32x4dFPN", "MobileNetV2FPN"])
 def test_heads_match_reference_golden(golden_dir, backbone):
     g = np.load(os.path.join(golden_dir, "model_%s.npz" % backbone))
     m = Model(backbone, classes=int(g["classes"]))
@@ -211,7 +211,8 @@ def _match_rate(got, ref, size, score_tol=1e-3, box_tol=1e-3):
 @pytest.mark.parametrize("backbone,shape,rotated", [("ResNet50FPN", (2, 3, 256, 384), False), ("ResNet101FPN", (1, 3, 128, 256), False),
                                                     ("ResNet34FPN", (1, 3, 128, 128), False), ("ResNet152FPN", (1, 3, 128, 128), False),
                                                     ("ResNet18FPN", (1, 3, 256, 256), True), ("ResNet50FPN", (1, 3, 160, 224), False),
-                                                    ("ResNeXt50_32x4dFPN", (1, 3, 256, 256), False), ("ResNeXt101_32x8dFPN", (1, 3, 128, 128), False)])
+                                                    ("ResNeXt50_32x4dFPN", (1, 3, 256, 256), False), ("ResNeXt101_32x8dFPN", (1, 3, 128, 128), False),
+                                                    ("MobileNetV2FPN", (2, 3, 256, 384), False)])
 def test_heads_match_fp16_emulating_oracle(backbone, shape, rotated):
     na = 27 if rotated else 9
     sd = make_state_dict(backbone, 5, na, rotated, 3)

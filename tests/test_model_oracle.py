@@ -11,7 +11,7 @@ from oracle import model_ref
 from retinanet_examples_b200.model import conv_specs, make_state_dict
 
 
-@pytest.mark.parametrize("backbone", ["ResNet18FPN", "ResNet50FPN", "ResNeXt50_32x4dFPN"])
+@pytest.mark.parametrize("backbone", ["ResNet18FPN", "ResNet50FPN", "ResNeXt50_32x4dFPN", "MobileNetV2FPN"])
 def test_model_ref_matches_reference_golden(golden_dir, backbone):
     g = np.load(os.path.join(golden_dir, "model_%s.npz" % backbone))
     sd = make_state_dict(backbone, int(g["classes"]), 9, False, int(g["seed"]))
