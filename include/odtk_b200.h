@@ -260,6 +260,13 @@ typedef struct {
    * xproj != NULL the kernel computes identity = xproj [n, h, width, 64] x wproj [c2, 64]^T itself on the tensor core
    * (residual is ignored, b3 must already include the projection's bias); c1 must be 64.                          */
   const void *xproj, *wproj;
+  /* GEMM3 (optional, c1 == 64, no projection): the NEXT block's conv1 -- z = relu(w_next [c_next, c2] x y + b_next), c_next in
+   * {64, 128} -- computed from the block output while its chunks are still in shared memory; z: NHWC fp16
+   * [n, h, width, c_next].  y is written as usual (it is the next block's identity).                               */
+  const void *w_next;
+  const float *b_next;
+  void *z;
+  int c_next;
 } odtk_bneck_t;
 int odtk_bottleneck_tail(const odtk_bneck_t *desc, odtk_stream_t stream);
 /* bias [cout] fp32 -> out [cout, 64] fp16 = (hi, lo, 0, ...) with hi + lo == bias to 2^-22 relative.       */

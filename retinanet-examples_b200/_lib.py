@@ -119,7 +119,8 @@ class BneckDesc(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("w2", ctypes.c_void_p), ("w3", ctypes.c_void_p), ("residual", ctypes.c_void_p),
                 ("b2", ctypes.c_void_p), ("b3", ctypes.c_void_p), ("y", ctypes.c_void_p),
                 ("n", ctypes.c_int), ("h", ctypes.c_int), ("width", ctypes.c_int), ("c1", ctypes.c_int), ("c2", ctypes.c_int),
-                ("relu", ctypes.c_int), ("xproj", ctypes.c_void_p), ("wproj", ctypes.c_void_p)]
+                ("relu", ctypes.c_int), ("xproj", ctypes.c_void_p), ("wproj", ctypes.c_void_p),
+                ("w_next", ctypes.c_void_p), ("b_next", ctypes.c_void_p), ("z", ctypes.c_void_p), ("c_next", ctypes.c_int)]
 
 
 class CandSink(ctypes.Structure):

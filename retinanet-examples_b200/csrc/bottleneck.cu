@@ -12,6 +12,9 @@
 //   ep1       epilogue warps: acc1 + b2 -> ReLU -> fp16 -> shared memory, written directly in the K-major SWIZZLE_128B
 //             layout of a UMMA A operand ("y1").
 //   GEMM2     1x1: for every 128-channel output tile n2: acc2[n2 & 1] = y1 * W3[n2]^T.
+//   GEMM3     (optional, C1 = 64) the NEXT block's conv1: z = relu(y * W1n^T + b1n) -- the block output chunks the epilogue
+//             has just written in place in the identity slots are already A operands; issued one tile late, behind the next
+//             tile's 3x3, into a third accumulator (columns 128 .. 255); removes the widest read of the next block.
 //   ep2       the identity chunks [128 px x 64 ch] arrive by TMA (4-D box straight from the NHWC tensor, 128B-swizzled rows
 //             = pixels) in a ring of 16 KB slots; each epilogue thread adds ITS pixel's 128 bytes to acc2 + b3, applies
 //             ReLU and writes the fp16 result back IN PLACE; the slot's 4 KB quarter of the warp is then the source of a
@@ -44,7 +47,7 @@ constexpr int kRSlot = 16384;                  // identity chunk: 128 pixels x 6
 constexpr int kMaxRSlots = 6;
 constexpr int kWSlot = 8192;                   // streamed weight block: this CTA's 64 rows x 64 K
 constexpr int kMaxWSlots = 8;
-constexpr int kBiasBytes = 2560;               // b2 (<= 128 fp32) + b3 (<= 512 fp32)
+constexpr int kBiasBytes = 3072;               // b2 (<= 128 fp32) + b3 (<= 512 fp32) + b_next (<= 128 fp32)
 constexpr int kBarBytes = 512;
 constexpr int kTmemCols = 512;
 constexpr int kSmemMax = 232448;               // 227 KB
@@ -72,7 +75,9 @@ struct BtBars {
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t acc2_full[2], acc2_empty[2];
   uint64_t y1_full[2], y1_empty[2], wres_full;
-  uint64_t xfull[2], xempty[2];          // projection mode: the block input tile (A operand of the identity GEMM)
+  uint64_t xfull[2], xempty[2];
+  uint64_t ycf[kMaxRSlots];              // GEMM3: the block output chunk in this slot is written (8 epilogue warps of the pair)
+  uint64_t acc3_full, acc3_empty;          // projection mode: the block input tile (A operand of the identity GEMM)
   uint32_t tmem_base;
 };
 static_assert(sizeof(BtBars) <= kBarBytes, "barrier block too small");
@@ -85,6 +90,11 @@ struct BtParams {
   int w_resident;        // C1 == 64: W2 / W3 halves stay in shared memory (52 KB); else they stream through the weight ring
   int nw, nr;            // weight / identity ring depths
   int relu;
+  int g3_late;           // issue GEMM3(t) behind G1(t+2) instead of right behind G2(t)
+  int n3;                // > 0: GEMM3 -- the NEXT block's 1x1 conv1 (C2 -> n3 channels, + bias + ReLU) computed from the block
+                         // output while its chunks still sit in the identity slots; z: [N, H, W, n3]
+  __half *z;
+  const float *b_next;
   int proj;              // identity = 1x1 projection of a 64-channel block input, computed here (first block of layer1)
   const float *b2, *b3;
 };
@@ -104,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2,
                        const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmR,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWd,
+                       const __grid_constant__ CUtensorMap tmW1,
                        const __grid_constant__ BtParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -114,8 +125,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const int nb1 = 9 * kc1;                           // W2 blocks per tile, linear index b = chunk * 9 + tap
   unsigned char *spatch = smem;
   unsigned char *sw = spatch + kNPatch * p.patch_slot;
-  const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot + (p.proj ? (uint32_t)n2tiles * kWSlot : 0u)
+  const uint32_t w_bytes = p.w_resident ? (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot + (p.proj ? (uint32_t)n2tiles * kWSlot : 0u) + (uint32_t)(2 * n2tiles) * (uint32_t)(p.n3 >> 1) * 128u
                                         : (uint32_t)p.nw * kWSlot;
+  const uint32_t w1_off = (uint32_t)nb1 * w2_block + (uint32_t)(n2tiles * kc1) * kWSlot + (p.proj ? (uint32_t)n2tiles * kWSlot : 0u);   // resident W1n blocks
   unsigned char *sres = sw + w_bytes;
   unsigned char *sx = sres + p.nr * kRSlot;          // projection mode: 2 slots for the block-input tile
   unsigned char *sy1 = sx + (p.proj ? 2 * kRSlot : 0);
@@ -135,7 +147,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kNPatch; s++) { mbar_init(&bars->pfull[s], 1); mbar_init(&bars->pempty[s], 1); }
     for (int s = 0; s < kMaxWSlots; s++) { mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
-    for (int s = 0; s < kMaxRSlots; s++) { mbar_init(&bars->rfull[s], 1); mbar_init(&bars->rempty[s], 4); }   // a slot is consumed by the 4 epilogue warps of one column half
+    for (int s = 0; s < kMaxRSlots; s++) { mbar_init(&bars->rfull[s], 1); mbar_init(&bars->rempty[s], p.n3 ? 5 : 4); mbar_init(&bars->ycf[s], 2 * 4); }
+    mbar_init(&bars->acc3_full, 1); mbar_init(&bars->acc3_empty, 2 * kEpiWarps);   // a slot is consumed by the 4 epilogue warps of one column half
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 2 * kEpiWarps);   // one arrival per epilogue warp of the pair
       mbar_init(&bars->acc2_full[b], 1); mbar_init(&bars->acc2_empty[b], 2 * kEpiWarps);
@@ -150,6 +163,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
     for (int i = lane; i < p.C1; i += 32) sbias[i] = p.b2 ? p.b2[i] : 0.0f;
     for (int i = lane; i < p.C2; i += 32) sbias[128 + i] = p.b3 ? p.b3[i] : 0.0f;
+    for (int i = lane; i < p.n3; i += 32) sbias[640 + i] = p.b_next ? p.b_next[i] : 0.0f;
   }
   tc_fence_before();
   cluster_sync_all();
@@ -190,6 +204,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       if (p.proj)
         for (int n2 = 0; n2 < n2tiles; n2++)
           tma2_load_2d(sw + nb1 * w2_block + (n2tiles * kc1 + n2) * kWSlot, &tmWd, lbar, 0, n2 * 128 + crank * 64);
+      if (p.n3)   // next block's conv1: [n3, C2], this CTA's half of the rows, one 64-channel K block per output chunk
+        for (int c = 0; c < 2 * n2tiles; c++)
+          tma2_load_2d(sw + w1_off + c * ((p.n3 >> 1) * 128), &tmW1, lbar, c * 64, crank * (p.n3 >> 1));
     }
     auto produce_g1 = [&](int pair) {
       int img, h0, w0;
@@ -272,14 +289,14 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       int it1 = 0, it2 = 0, u2 = 0;                  // G1 / G2 invocation counters, acc2 use counter
       int xs = 0;
       uint32_t xph = 0;
-      const uint32_t x_s = smem_u32(sx);
+      const uint32_t x_s = smem_u32(sx), res_s3 = smem_u32(sres);
       if (p.w_resident) mbar_wait(&bars->wres_full, 0);
       tc_fence_after();
       auto issue_g1 = [&]() {
         const int buf = it1 & 1;
         BT_WAIT(0, &bars->acc1_empty[buf], ((uint32_t)(it1 >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 128);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.C1);   // acc1[2] at columns 0 / C1 (C1 = 64: columns 128 .. 255 stay free for GEMM3's accumulator)
         for (int kc = 0; kc < kc1; kc++) {
           BT_WAIT(1, &bars->pfull[pb], pphase);
           tc_fence_after();
@@ -351,11 +368,41 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         it2++;
       };
       BT_TOTAL_BEGIN();
+      int it3 = 0;
+      auto issue_g3 = [&]() {
+          // GEMM3: z = y * W1n^T over the block output chunks the epilogue has just written in place into the identity
+          // slots (K-major, 128-byte swizzle: already an A operand); a slot goes back to its producer when these MMAs AND
+          // the chunk's bulk stores have read it
+          const uint32_t idesc3 = (1u << 4) | ((uint32_t)(p.n3 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+          mbar_wait(&bars->acc3_empty, ((uint32_t)it3 & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_z = tmem_base + 128u;
+          for (int c = 0; c < 2 * n2tiles; c++) {
+            const int cidx = 2 * n2tiles * it3 + c, slot = cidx % p.nr;
+            mbar_wait(&bars->ycf[slot], (uint32_t)(cidx / p.nr) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = make_desc_kmajor(res_s3 + (uint32_t)(slot * kRSlot), 128);
+              const uint64_t db = make_desc_kmajor(w_s + w1_off + (uint32_t)c * (uint32_t)((p.n3 >> 1) * 128), 128);
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma2_f16(tmem_z, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc3, (c | k) ? 1u : 0u);
+              tc_commit2_mc(&bars->rempty[slot], (uint16_t)3);
+            }
+          }
+          if (elect_one()) tc_commit2_mc(&bars->acc3_full, (uint16_t)3);
+        it3++;
+      };
+      // order on the tensor pipe: G1(t+1), [G3(t-1)], G2(t): GEMM3 of a tile is issued one step late (g3_late), behind the
+      // next tile's 3x3, so that the pipe has work while the epilogue writes the block output the GEMM3 reads
       if (c_first < npairs) issue_g1();
+      bool g3_pending = false;
       for (int pair = c_first; pair < npairs; pair += c_step) {
         if (pair + c_step < npairs) issue_g1();
+        if (g3_pending) { issue_g3(); g3_pending = false; }
         issue_g2();
+        if (p.n3) { if (p.g3_late) g3_pending = true; else issue_g3(); }
       }
+      if (g3_pending) issue_g3();
       BT_TOTAL_END(6);
     }
   } else if (warp >= 4) {
@@ -373,7 +420,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       BT_WAIT(12, &bars->acc1_full[buf], (uint32_t)(it >> 1) & 1u);
       BT_WAIT(13, &bars->y1_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + sg * cols1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.C1 + sg * cols1);
       const uint32_t yrow = y1_s + (uint32_t)(buf * kc1) * 16384u + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
       uint32_t v[2][16];
       const int nch = cols1 >> 4;                    // 16-column chunks: 2 (C1 = 64) or 4 (C1 = 128)
@@ -489,6 +536,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         BT_ADD(19, tc_);
         BT_T0(td_);
         if (lane == 0) {
+          if (p.n3) mbar_arrive_remote(mapa_rank(smem_u32(&bars->ycf[slot]), 0));   // GEMM3 may read this warp's quarter of the chunk
           mbar_arrive_remote(buf ? lbar_acc2e1 : lbar_acc2e0);   // the accumulator has been read: hand it back (one arrival per warp)
           if (real) {
             // 32 pixels = 8 rows x 4 columns of the tile = this warp's 4 KB quarter of the slot; pixels outside the image
@@ -504,13 +552,61 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         BT_ADD(20, td_);
       }
     };
+    // ---- ep3 (GEMM3): acc3 + b_next -> ReLU -> fp16 -> z, 16-byte stores straight from registers (a quarter of y's bytes) ----
+    auto ep3 = [&](int pair, int t) {
+      int img, h0, w0;
+      const bool real = tile_of(pair, img, h0, w0);
+      mbar_wait(&bars->acc3_full, (uint32_t)t & 1u);
+      tc_fence_after();
+      const int cols3 = p.n3 >> 1;                   // this warp's columns of acc3: [sg * cols3, +cols3)
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(sg * cols3);
+      const int hh = h0 + (row & 7), ww = w0 + (row >> 3);
+      const bool inside = real && hh < p.H && ww < p.W;
+      __half *zrow = p.z + (((long long)img * p.H + hh) * p.W + ww) * p.n3 + sg * cols3;
+      uint32_t v[2][16];
+      const int nch = cols3 >> 4;
+      tc_ld16(taddr, v[0]);
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        if (cc < nch) {
+          tc_ld_wait();
+          if (cc + 1 < nch) tc_ld16(taddr + (uint32_t)((cc + 1) * 16), v[(cc + 1) & 1]);
+          const int col0 = sg * cols3 + cc * 16;
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b = lds128f(sb_s + (uint32_t)((640 + col0 + j4 * 4) * 4));
+            f[4 * j4] = __uint_as_float(v[cc & 1][4 * j4]) + b.x;
+            f[4 * j4 + 1] = __uint_as_float(v[cc & 1][4 * j4 + 1]) + b.y;
+            f[4 * j4 + 2] = __uint_as_float(v[cc & 1][4 * j4 + 2]) + b.z;
+            f[4 * j4 + 3] = __uint_as_float(v[cc & 1][4 * j4 + 3]) + b.w;
+          }
+          uint4 o0, o1;
+          __half2 *q0 = reinterpret_cast<__half2 *>(&o0), *q1 = reinterpret_cast<__half2 *>(&o1);
+          const __half2 z2 = __float2half2_rn(0.0f);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            q0[j] = __hmax2(__floats2half2_rn(f[2 * j], f[2 * j + 1]), z2);
+            q1[j] = __hmax2(__floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]), z2);
+          }
+          if (inside) {
+            *reinterpret_cast<uint4 *>(zrow + cc * 16) = o0;
+            *reinterpret_cast<uint4 *>(zrow + cc * 16 + 8) = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&bars->acc3_empty), 0));
+    };
     // software pipeline, mirrored by the MMA warp: ep1(t+1) (feeds GEMM2(t+1)) before ep2(t)
-    int it = 0;
+    int it = 0, t3 = 0;
     BT_TOTAL_BEGIN();
     if (c_first < npairs) ep1(it++);
     for (int pair = c_first; pair < npairs; pair += c_step) {
       if (pair + c_step < npairs) ep1(it++);
       ep2(pair);
+      if (p.n3) ep3(pair, t3++);
     }
     if (held >= 0 && lane == 0) {
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -582,6 +678,8 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   if (!d || !d->x || !d->w2 || !d->w3 || !d->y) return ODTK_E_INVALID;
   const bool proj = d->xproj != nullptr;
   if (proj ? (!d->wproj || d->c1 != 64) : !d->residual) return ODTK_E_INVALID;
+  const int n3 = d->w_next ? d->c_next : 0;
+  if (n3 && (proj || d->c1 != 64 || !d->z || (n3 != 64 && n3 != 128) || (((uintptr_t)d->w_next | (uintptr_t)d->z) & 15))) return ODTK_E_UNSUPPORTED;
   if (d->n <= 0 || d->h <= 0 || d->width <= 0) return ODTK_E_INVALID;
   if ((d->c1 != 64 && d->c1 != 128) || d->c2 % 128 != 0 || d->c2 <= 0 || d->c2 > 512) return ODTK_E_UNSUPPORTED;
   if (((uintptr_t)d->x | (uintptr_t)d->w2 | (uintptr_t)d->w3 | (uintptr_t)d->residual | (uintptr_t)d->y | (uintptr_t)d->xproj | (uintptr_t)d->wproj) & 15) return ODTK_E_INVALID;
@@ -606,9 +704,12 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   p.patch_slot = (18 * pitch * 128 + 1023) / 1024 * 1024;
   p.w_resident = d->c1 == 64;
   p.proj = proj ? 1 : 0;
+  p.n3 = n3; p.z = (__half *)d->z; p.b_next = d->b_next;
+  { static int late = -1; if (late < 0) { const char *e = getenv("ODTK_BNECK_G3_LATE"); late = e ? atoi(e) : 1; } p.g3_late = late; }   // measured: 491.6 vs 552.1 us per launch
   const int kc1 = d->c1 / 64, n2tiles = d->c2 / 128;
-  const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot + (proj ? n2tiles * kWSlot : 0);
-  if (p.w_resident && w_resident_bytes > 72 * 1024) p.w_resident = 0;
+  const int w_resident_bytes = 9 * kc1 * (d->c1 / 2) * 128 + n2tiles * kc1 * kWSlot + (proj ? n2tiles * kWSlot : 0) + 2 * n2tiles * (n3 / 2) * 128;
+  if (p.w_resident && w_resident_bytes > 88 * 1024) p.w_resident = 0;
+  if (n3 && !p.w_resident) return ODTK_E_UNSUPPORTED;
   if (proj && !p.w_resident) return ODTK_E_UNSUPPORTED;
   const int fixed = 1024 + kNPatch * p.patch_slot + 2 * kc1 * 16384 + kBiasBytes + kBarBytes + (proj ? 2 * kRSlot : 0);
   // shared-memory budget: identity ring as deep as it gets (it carries the HBM stream), then the weight ring
@@ -626,7 +727,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   p.relu = d->relu;
   p.b2 = d->b2; p.b3 = d->b3;
   const uint64_t C1 = (uint64_t)d->c1, C2 = (uint64_t)d->c2, H = (uint64_t)d->h, W = (uint64_t)d->width, N = (uint64_t)d->n;
-  CUtensorMap tmX, tmW2, tmW3, tmR, tmY, tmWd;
+  CUtensorMap tmX, tmW2, tmW3, tmR, tmY, tmWd, tmW1;
   {
     uint64_t dims[4] = {C1, H, W, N}, str[3] = {W * C1 * 2, C1 * 2, H * W * C1 * 2};
     uint32_t box[4] = {64, (uint32_t)p.ppitch, 18, 1};
@@ -649,6 +750,12 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
     if (!proj && !bt_encode(&tmR, d->residual, 4, dims, str, boxR)) return ODTK_E_CUDA;
   }
   tmWd = tmW3;
+  tmW1 = tmW3;
+  if (n3) {   // next block's conv1 weights [n3, C2]: this CTA's half of the rows, 64-channel K blocks
+    uint64_t dimsW[2] = {C2, (uint64_t)n3}, strW[1] = {C2 * 2};
+    uint32_t boxW[2] = {64, (uint32_t)(n3 / 2)};
+    if (!bt_encode(&tmW1, d->w_next, 2, dimsW, strW, boxW)) return ODTK_E_CUDA;
+  }
   if (proj) {   // identity = xproj [n, h, width, 64] x wproj [c2, 64]^T, computed by the kernel
     uint64_t dims[4] = {64, H, W, N}, str[3] = {W * 64 * 2, 64 * 2, H * W * 64 * 2};
     uint32_t boxR[4] = {64, 8, 16, 1};
@@ -675,7 +782,7 @@ extern "C" int odtk_bottleneck_tail(const odtk_bneck_t *d, odtk_stream_t stream_
   cfg.numAttrs = odtk_pdl_on() ? 2 : 1;
   {
     OdtkProfScope prof(ODTK_PROF_CONV, stream);
-    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmWd, p);
+    cudaLaunchKernelEx(&cfg, bottleneck_tail_kernel, tmX, tmW2, tmW3, tmR, tmY, tmWd, tmW1, p);
   }
   return cudaGetLastError() == cudaSuccess ? ODTK_OK : ODTK_E_CUDA;
 }

@@ -275,7 +275,7 @@ def stem_pool_padded(xp, h, wd, w, bias, cout, relu=True):
     return out
 
 
-def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None, wproj=None):
+def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None, wproj=None, w_next=None, b_next=None):
     """Tail of a stride-1 bottleneck block in one kernel (odtk_bottleneck_tail):
     relu(conv1x1(relu(conv3x3(x, w2) + b2), w3) + b3 + residual).  x: NHWC fp16 [N,H,W,C1] (C1 64 / 128); w2 packed
     [C1, 9*C1]; w3 packed [C2, C1]; residual NHWC fp16 [N,H,W,C2].  Returns NHWC fp16 [N,H,W,C2]."""
@@ -296,6 +296,11 @@ def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None
     d.b2 = b2.data_ptr() if b2 is not None else None
     d.b3 = b3.data_ptr() if b3 is not None else None
     d.n, d.h, d.width, d.c1, d.c2, d.relu = n, h, wd, c1, c2, int(relu)
+    z = None
+    if w_next is not None:          # GEMM3: the next block's conv1 (+ bias + ReLU) from the block output, in the same kernel
+        z = torch.empty((n, h, wd, w_next.shape[0]), dtype=torch.float16, device=x.device)
+        d.w_next, d.z, d.c_next = w_next.data_ptr(), z.data_ptr(), w_next.shape[0]
+        d.b_next = b_next.data_ptr() if b_next is not None else None
     _lib.check(_lib.lib().odtk_bottleneck_tail(ctypes.byref(d), _stream()), "bottleneck_tail")
     STATS["launches"] += 1
     px = n * h * wd
@@ -303,9 +308,10 @@ def bottleneck_tail(x, w2, b2, w3, b3, residual, relu=True, out=None, xproj=None
         _trace("bneck_tail", 2 * px * (c1 * (9 * c1 + c2) + 64 * c2), px * (c1 + 64 + c2) * 2 + w2.numel() * 2 + w3.numel() * 2 + wproj.numel() * 2,
                n=n, h=h, w=wd, cin=c1, cout=c2, upsample=False, residual=False)
     else:
-        _trace("bneck_tail", 2 * px * c1 * (9 * c1 + c2), px * (c1 + 2 * c2) * 2 + w2.numel() * 2 + w3.numel() * 2,
-               n=n, h=h, w=wd, cin=c1, cout=c2, residual=True)
-    return out
+        c3 = w_next.shape[0] if w_next is not None else 0
+        _trace("bneck_tail", 2 * px * (c1 * (9 * c1 + c2) + c2 * c3), px * (c1 + 2 * c2 + c3) * 2 + w2.numel() * 2 + w3.numel() * 2,
+               n=n, h=h, w=wd, cin=c1, cout=c2, residual=True, upsample=bool(c3))
+    return out if z is None else (out, z)
 
 
 def depthwise3x3(x, w, bias, stride=1, act=2):

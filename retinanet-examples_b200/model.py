@@ -229,6 +229,7 @@ class Model:
         self.fused_stem = os.environ.get("ODTK_FUSED_STEM", "1") != "0"
         self.merged_heads = os.environ.get("ODTK_MERGED_HEADS", "1") != "0"
         self.fused_bneck = os.environ.get("ODTK_FUSED_BNECK", "1") != "0"
+        self.fused_conv1 = os.environ.get("ODTK_FUSED_CONV1", "1") != "0"
         self._atlas = {}
         self._fused = {}
         self._head_streams = None
@@ -459,9 +460,12 @@ class Model:
             return self._features_mobilenet(x)
         P = self._packed
         outs = {}
-        for blk in P["blocks"]:
+        blocks = P["blocks"]
+        z_next = None                 # conv1 of THIS block, already computed by the previous block's fused tail (GEMM3)
+        for bi, blk in enumerate(blocks):
             cs = blk["convs"]
             dn = blk["down"]
+            z_in, z_next = z_next, None
             if (self.fused_bneck and dn is not None and len(cs) == 3 and dn.ks == 1 and dn.stride == 1 and dn.cin == 64 and
                     dn.groups == 1 and cs[1].stride == 1 and cs[1].groups == 1 and cs[1].ks == 3 and cs[1].cin == 64 and
                     cs[1].cout == 64 and cs[2].cin == 64 and cs[2].cout == dn.cout and dn.cout % 128 == 0 and dn.cout <= 512):
@@ -481,13 +485,22 @@ class Model:
                     cs[1].cin in (64, 128) and cs[1].cout == cs[1].cin and cs[2].cin == cs[1].cin and cs[2].cout % 128 == 0 and
                     cs[2].cout <= 512):
                 # conv2 (3x3) + conv3 (1x1) + identity + ReLU in one kernel: the 3x3's output never leaves the SM
-                out = cs[0](x, relu=True)
+                out = z_in if z_in is not None else cs[0](x, relu=True)
                 px = out.shape[0] * out.shape[1] * out.shape[2]
                 engine.STATS["conv_flops"] += 2 * px * cs[1].cin * (9 * cs[1].cin + cs[2].cout)
-                x = engine.bottleneck_tail(out, cs[1].w, cs[1].b, cs[2].w, cs[2].b, identity, relu=True)
+                # GEMM3: the NEXT block's conv1 (1x1, C2 -> 64 / 128, + ReLU) from this block's output while it is still in
+                # shared memory -- removes a full read of the widest tensor of the level
+                nxt = blocks[bi + 1]["convs"] if bi + 1 < len(blocks) else None
+                if (self.fused_conv1 and cs[1].cin == 64 and nxt is not None and len(nxt) == 3 and nxt[0].ks == 1 and nxt[0].stride == 1 and
+                        nxt[0].groups == 1 and nxt[0].cin == cs[2].cout and nxt[0].cout in (64, 128) and nxt[0].b is not None):
+                    engine.STATS["conv_flops"] += 2 * px * nxt[0].cin * nxt[0].cout
+                    x, z_next = engine.bottleneck_tail(out, cs[1].w, cs[1].b, cs[2].w, cs[2].b, identity, relu=True,
+                                                       w_next=nxt[0].w, b_next=nxt[0].b)
+                else:
+                    x = engine.bottleneck_tail(out, cs[1].w, cs[1].b, cs[2].w, cs[2].b, identity, relu=True)
             else:
-                out = x
-                for c in cs[:-1]:
+                out = z_in if z_in is not None else x
+                for c in (cs[1:-1] if z_in is not None else cs[:-1]):
                     out = c(out, relu=True)
                 x = cs[-1](out, relu=True, residual=identity)
             if blk["last"]:

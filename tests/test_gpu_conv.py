@@ -423,3 +423,22 @@ def test_conv1x1_n_tile_not_a_multiple_of_64():
     y = engine.conv2d(x.to(DEV), engine.pack_weight(wt.float()).to(DEV), bd, 960, 1, relu=2, bias_op=engine.pack_bias(bd))
     assert engine.last_plan()["bn"] == 240 and engine.last_plan()["tma_store"] == 0
     _close16(y, F.relu6(_ref_conv(x, wt, b, 1)))
+
+
+@pytest.mark.parametrize("n,h,w,c3", [(2, 24, 48, 64), (1, 9, 17, 64), (3, 8, 16, 128), (2, 200, 320, 64), (2, 200, 320, 128)])
+def test_bottleneck_tail_with_next_conv1(n, h, w, c3):
+    """GEMM3 of the fused tail kernel: the NEXT block's conv1 (1x1 + bias + ReLU) computed from the block output while its
+    chunks are still in shared memory; the block output itself must be unchanged."""
+    c1, c2 = 64, 256
+    g = torch.Generator().manual_seed(n * 13 + h + w + c3)
+    x = _rand((n, h, w, c1), g)
+    w2, b2 = _rand((c1, c1, 3, 3), g, 0.04), torch.randn(c1, generator=g) * 0.5
+    w3, b3 = _rand((c2, c1, 1, 1), g, 0.08), torch.randn(c2, generator=g) * 0.5
+    w1n, b1n = _rand((c3, c2, 1, 1), g, 0.06), torch.randn(c3, generator=g) * 0.5
+    res = _rand((n, h, w, c2), g)
+    args = (x.to(DEV), engine.pack_weight(w2.float()).to(DEV), b2.to(DEV), engine.pack_weight(w3.float()).to(DEV), b3.to(DEV), res.to(DEV))
+    y0 = engine.bottleneck_tail(*args, relu=True)
+    y, z = engine.bottleneck_tail(*args, relu=True, w_next=engine.pack_weight(w1n.float()).to(DEV), b_next=b1n.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(y, y0)
+    _close16(z, _ref_conv(y0.cpu(), w1n, b1n, 1, relu=True))
