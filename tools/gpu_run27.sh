@@ -21,7 +21,7 @@ python tools/layer_table.py $O/step_launches.csv $O/step_trace.json --out $O/lay
 head -12 $O/layer_table.txt
 # ncu full captures: the fused bottleneck kernel (C1 = 64), the head tower launch, the class-head final launch
 timeout 300 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:bottleneck_tail -s 1 -c 1 -f -o $O/ncu_bneck_l1 python tools/capture_step.py > $O/ncu_bneck.log 2>&1
-timeout 300 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:conv_gemm -s 46 -c 1 -f -o $O/ncu_tower python tools/capture_step.py > $O/ncu_tower.log 2>&1
+
 # compute-sanitizer on the conv / bottleneck cases
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_cases.py conv > $O/sanitizer_memcheck_conv.log 2>&1
 tail -3 $O/sanitizer_memcheck_conv.log

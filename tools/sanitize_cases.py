@@ -61,6 +61,17 @@ def main():
                 engine.bottleneck_tail(xx, w2, b2, w3, b3, rnd(3, 9, 17, c2))
             torch.cuda.synchronize()
             print("bottleneck_tail c1=%d proj=%s ok" % (c1, proj), flush=True)
+        for c3 in (64, 128):                                               # + GEMM3: the next block's conv1 from the block output
+            xx, w2 = rnd(3, 9, 17, 64), engine.pack_weight(torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(DEV)
+            w3 = engine.pack_weight(torch.randn((256, 64, 1, 1), generator=g) * 0.05).to(DEV)
+            wn = engine.pack_weight(torch.randn((c3, 256, 1, 1), generator=g) * 0.05).to(DEV)
+            engine.bottleneck_tail(xx, w2, torch.randn(64, generator=g).to(DEV), w3, torch.randn(256, generator=g).to(DEV), rnd(3, 9, 17, 256),
+                                   w_next=wn, b_next=torch.randn(c3, generator=g).to(DEV))
+            torch.cuda.synchronize()
+            print("bottleneck_tail + next conv1 (%d) ok" % c3, flush=True)
+        engine.depthwise3x3(rnd(2, 9, 11, 192), rnd(9, 192), torch.randn(192, generator=g).to(DEV), stride=2, act=2)
+        conv(1, 4, 4, 192, 960, 1, relu=2)                                 # ReLU6, 240-wide N tiles (row-store epilogue)
+        torch.cuda.synchronize()
         x = rnd(2, 64, 96, 3)
         wt, b = engine.pack_stem_weight(torch.randn((64, 3, 7, 7), generator=g) * 0.1).to(DEV), torch.randn(64, generator=g).to(DEV)
         engine.stem_pool(x, wt, b, 64)
