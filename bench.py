@@ -366,6 +366,22 @@ class PostprocWorkload:
         self.nstreams = int(os.environ.get("ODTK_BENCH_POSTPROC_STREAMS", "3"))
         self.streams = [torch.cuda.Stream(device=device) for _ in range(self.nstreams)] if self.nstreams > 1 else []
         self.k = 0
+        self.graphs = []
+
+    def _capture(self):
+        """One CUDA graph of the step per stream (its own output / workspace buffers): the five launches of a step take
+        less GPU time than their host-side enqueue, so the pipelined mode replays graphs."""
+        torch = self.torch
+        for s in self.streams:
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._run(self.dev)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                out = self._run(self.dev)
+            self.graphs.append((g, out))
 
     def _run(self, tensors):
         from retinanet_examples_b200 import _C
@@ -378,11 +394,19 @@ class PostprocWorkload:
             self.out = self._run(self.dev)
             return
         torch = self.torch
-        main, side = torch.cuda.current_stream(), self.streams[self.k % self.nstreams]
+        if not self.graphs:
+            self._capture()
+        i = self.k % self.nstreams
+        main, side = torch.cuda.current_stream(), self.streams[i]
         self.k += 1
         side.wait_stream(main)                    # ordered after whatever the caller enqueued (the timing start event)
         with torch.cuda.stream(side):
-            self.out = self._run(self.dev)
+            self.graphs[i][0].replay()
+        self.out = self.graphs[i][1]
+
+    def step_profile(self):
+        """Eager, one stream: the library's per-kernel event brackets see every launch (roofline pass, latency)."""
+        self.out = self._run(self.dev)
 
     def drain(self):
         """The caller's stream waits for every batch still in flight (called before the timing end event)."""
@@ -452,13 +476,13 @@ CONFIGS = {
 
 def postproc_sub(device, peaks, lib, rotated=False, batch=8, steps=30):
     """decode + NMS alone (the second half of BASELINE.json's metric, configs[1]: head outputs of 8 images, fp32 NCHW entry
-    points): microseconds per image, device-timed, plus the streaming kernel's HBM roofline."""
+    points): microseconds per image, device-timed -- throughput with 3 batches in flight (CUDA graphs on 3 streams) and
+    one batch at a time (eager, per-kernel event brackets) -- plus the streaming kernel's HBM roofline."""
     import torch
     wl = PostprocWorkload(batch, 0, device, rotated)
     for _ in range(3):
         wl.step()
-    lib.odtk_prof_reset()
-    lib.odtk_prof_enable(1)
+    wl.drain()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -467,27 +491,30 @@ def postproc_sub(device, peaks, lib, rotated=False, batch=8, steps=30):
     wl.drain()
     e1.record()
     torch.cuda.synchronize()
-    lib.odtk_prof_enable(0)
     ms = e0.elapsed_time(e1)
+    # the same batches one after the other on one stream, eagerly, every kernel bracketed by events
+    for _ in range(2):
+        wl.step_profile()
+    lib.odtk_prof_reset()
+    lib.odtk_prof_enable(1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        wl.step_profile()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.odtk_prof_enable(0)
+    serial_ms = e0.elapsed_time(e1)
     roof = wl.roofline(lib, peaks, steps)
     nms_ms, nms_n = _prof_get(lib, 2)
     sel_ms, sel_n = _prof_get(lib, 1)
-    # the same batches one after the other on one stream: the latency of a batch (what round 1 reported as us/image)
-    saved, wl.streams = wl.streams, []
-    e0.record()
-    for _ in range(steps):
-        wl.step()
-    e1.record()
-    torch.cuda.synchronize()
-    wl.streams = saved
-    serial_ms = e0.elapsed_time(e1)
     return {"workload": wl.name, "us_per_image": round(ms * 1e3 / steps / batch, 2), "images_per_gpu": batch, "steps": steps,
             "batches_in_flight": max(1, wl.nstreams), "latency_us_per_batch": round(serial_ms * 1e3 / steps, 1),
             "us_per_image_one_batch_at_a_time": round(serial_ms * 1e3 / steps / batch, 2),
             "images_per_sec": round(batch * steps / (ms * 1e-3), 1),
             "hbm_floor_us_per_image": round(sum(wl.level_score_bytes) / batch / (peaks["hbm"] * 1e9) * 1e6, 2),
             "nms_us_per_launch": round(nms_ms * 1e3 / max(nms_n, 1), 2), "select_decode_us_per_step": round(sel_ms * 1e3 / steps, 2),
-            "note": "per-kernel times come from event-bracketed launches inside the same timed loop", "roofline": roof}
+            "note": "per-kernel times come from event-bracketed launches of the one-batch-at-a-time loop", "roofline": roof}
 
 
 def main():
