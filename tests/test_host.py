@@ -107,3 +107,32 @@ def test_plugin_shaped_wrappers_compile_and_query_sizes(tmp_path):
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "decode_ws=" in out and "format_ok=1" in out
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/odtk_b200.h must compile as C (no C++-isms, no torch / CUDA types)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "odtk_b200.h"\nint main(void) { odtk_conv_t c; odtk_bneck_t b; odtk_gather_t g; (void)c; (void)b; (void)g; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_state_dict_layouts_match_torchvision():
+    """make_state_dict / conv_specs follow the reference's key layout: `backbones.<Name>.features.` + the torchvision module's
+    own keys (odtk/backbones/resnet.py:7-22, mobilenet.py:5-13), same shapes; only the classification tails the reference
+    never runs (fc / features.18 / classifier) are absent."""
+    import torchvision.models as tvm
+    from retinanet_examples_b200.model import make_state_dict
+    for name, ctor in (("ResNet50FPN", tvm.resnet50), ("ResNeXt50_32x4dFPN", tvm.resnext50_32x4d), ("MobileNetV2FPN", tvm.mobilenet_v2)):
+        ref = ctor(weights=None).state_dict()
+        sd = make_state_dict(name, 3, 9, False, seed=0)
+        pre = "backbones.%s.features." % name
+        ours = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        skip = ("num_batches_tracked", "fc.", "features.18.", "classifier.")
+        want = {k: v for k, v in ref.items() if not any(t in k for t in skip)}
+        assert set(ours) == set(want), (name, sorted(set(want) ^ set(ours))[:5])
+        for k, v in want.items():
+            assert tuple(ours[k].shape) == tuple(v.shape), (name, k)
