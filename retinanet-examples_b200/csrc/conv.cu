@@ -33,7 +33,13 @@
 //   5  7x7 stride-2 stem, "raw window": the zero-padded NHWC4 image patch is read by the tensor core as an
 //      un-swizzled K-major operand whose 16-byte row pitch is the distance between neighbouring windows
 //      (make_desc_raw); weights resident.   2 = the older overlapping-window 5-D TMA map (fallback).
-// Odd-sized strided convolutions are first lowered to GEMM rows by layers.cu and run as mode 0.
+// Stride-2 3x3 / 1x1 on odd sizes use element-strided TMA boxes (mode 1 with s2); only Cin % 64 != 0 callers (RGB stems other
+// than the fused 7x7) are first lowered to GEMM rows by layers.cu and run as mode 0.
+// Round 2: 128- and 256-wide 3x3 layers, deep 1x1 layers and narrow head outputs run as cta_group::2 CTA pairs; one launch
+// covers all five pyramid levels through a tile table (pyramid atlas); the candidate epilogue overlaps each slot
+// reservation with the next chunk; ReLU6 (relu == 2); kernels are launched with programmatic stream serialization
+// (griddepcontrol) so that a kernel's prologue runs under its predecessor's tail; remote barrier arrives are one per warp
+// with CTA-scope release.  The stride-1 bottleneck tails of layer1 / layer2 and the stem run in bottleneck.cu / stem.cu.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
