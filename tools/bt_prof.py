@@ -1,5 +1,6 @@
-"""Wait profile of bottleneck_tail_kernel (a -DODTK_BT_PROF build of the library, ODTK_B200_LIB=...): cycles each role of
-CTA 0 spends waiting on each barrier, per launch."""
+"""Wait profile of bottleneck_tail_kernel: cycles each role of CTA 0 spends waiting on each barrier, per launch.
+    make -C retinanet-examples_b200/csrc btprof
+    ODTK_B200_LIB=tools/_ab/lib_btprof.so python tools/bt_prof.py"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
