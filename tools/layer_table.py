@@ -71,7 +71,8 @@ def main():
     summary = {"launches": len(table), "sum_us": round(tot, 1), "sum_ideal_us": round(ideal, 1),
                "frac": round(ideal / tot, 4), "tensor_peak_tflops": tf, "hbm_peak_gbs": bw,
                "dram_bytes": sum(l.get("dram", 0.0) for l in launches),
-               "conv_dram_bytes": sum(l.get("dram", 0.0) for l in launches if "conv_gemm" in l["kernel"]),
+               "conv_dram_bytes": sum(l.get("dram", 0.0) for l in launches
+                                      if any(k in l["kernel"] for k in ("conv_gemm", "bottleneck_tail", "stem_pool"))),
                "groups": [dict(layer=k, share=round(g["us"] / tot, 4), eff=round(g["ideal_us"] / max(g["us"], 1e-9), 3),
                                **{a: round(b, 2) for a, b in g.items()})
                           for k, g in sorted(groups.items(), key=lambda kv: -kv[1]["us"])]}
